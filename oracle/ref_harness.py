@@ -1,0 +1,67 @@
+"""TEST INFRASTRUCTURE ONLY — imports the UNMODIFIED reference from /root/reference.
+
+Only usable in the build container (``/root/reference`` does not exist on the GPU box). It is used by
+``tests/golden/make_golden.py`` to generate the committed golden fixtures and by ``oracle/check_oracle_vs_reference.py``
+to pin the numpy restatement in ``oracle/morpho_oracle.py`` against the real thing. Nothing in the product package,
+``bench.py`` or the ``-m gpu`` tests imports this module.
+
+Mechanics: ``anndata`` is not installed, so a stub module exposing ``AnnData = AnnDataLite`` is registered; the
+package ``__init__`` files of ``spateo.alignment`` / ``spateo.alignment.methods`` import pyvista/POT (absent), so bare
+package modules are pre-registered and only ``methods/{backend,utils,morpho_class}.py`` are imported (unmodified).
+"""
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = "/root/reference"
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "spateo", "alignment", "methods"))
+
+
+_loaded = {}
+
+
+def load_reference():
+    """Return (morpho_class_module, utils_module) of the unmodified reference."""
+    if "mc" in _loaded:
+        return _loaded["mc"], _loaded["utils"]
+    if not reference_available():
+        raise RuntimeError("reference tree not present (expected only in the build container)")
+    repo_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if repo_root not in sys.path:
+        sys.path.insert(0, repo_root)
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+    if "anndata" not in sys.modules:
+
+        class _Stub(types.ModuleType):
+            def __getattr__(self, n):
+                if n.startswith("__"):
+                    raise AttributeError(n)
+                return lambda *a, **k: None
+
+        ad = _Stub("anndata")
+        ad.AnnData = AnnDataLite
+        sys.modules["anndata"] = ad
+
+    import spateo  # noqa: F401  (lazy loaders only)
+
+    for name, path in [
+        ("spateo.alignment", os.path.join(REFERENCE_ROOT, "spateo/alignment")),
+        ("spateo.alignment.methods", os.path.join(REFERENCE_ROOT, "spateo/alignment/methods")),
+    ]:
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [path]
+            sys.modules[name] = pkg
+    mc = importlib.import_module("spateo.alignment.methods.morpho_class")
+    utils = importlib.import_module("spateo.alignment.methods.utils")
+    _loaded["mc"], _loaded["utils"] = mc, utils
+    return mc, utils

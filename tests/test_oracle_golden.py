@@ -1,0 +1,104 @@
+"""CPU: pins oracle/morpho_oracle.py against golden vectors produced by executing the unmodified reference
+(tests/golden/make_golden.py). Bitwise in the build container; tolerances below allow for a different host BLAS."""
+
+import ast
+
+import numpy as np
+import pytest
+
+from oracle import morpho_oracle as mo
+
+CASES = ["2d_full", "3d_svi", "3d_full_warp", "2d_full_nonn_euc"]
+
+
+def _cfg(g):
+    return ast.literal_eval(str(g["cfg"]))
+
+
+def _relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def _make_oracle(g, dtype):
+    cfg = _cfg(g)
+    np.random.seed(0)
+    return mo.MorphoPairOracle(
+        np.asfortranarray(g["raw_coords_moving"]), np.asfortranarray(g["raw_coords_fixed"]),
+        [g["exp_moving"]], [g["exp_fixed"]], dtype=dtype, SVI_mode=cfg["svi"], max_iter=cfg["max_iter"], K=cfg["K"],
+        **cfg["kw"],
+    )
+
+
+def test_calc_distance_kl_matches_reference(golden):
+    g = golden("2d_full")
+    [d] = mo.calc_distance(g["exp_moving"], g["exp_fixed"], "kl")
+    assert d.dtype == np.float32
+    assert np.abs(d - g["exp_dist"]).max() <= 2e-6
+
+
+@pytest.mark.parametrize("case", ["2d_full", "3d_full_warp"])
+@pytest.mark.parametrize("it", [0, 95])
+def test_get_P_core_matches_reference_dump(golden, case, it):
+    g = golden(case)
+    XAHat, alpha, SigmaDiag = g[f"it{it}_in_XAHat"], g[f"it{it}_in_alpha"], g[f"it{it}_in_SigmaDiag"]
+    sigma2, gamma = g[f"it{it}_in_sigma2"], g[f"it{it}_in_gamma"]
+    sv = np.float32(g[f"it{it}_in_sigma2_variance"])
+    yb = g["pre_coordsB"]
+    [ed] = mo.calc_distance(g["exp_moving"], g["exp_fixed"], "kl")
+    P, kns, kn2, s2r = mo.get_P_core(
+        Dim=np.float32(yb.shape[1]), spatial_dist=mo.euc_distance(XAHat, yb), exp_dist=[ed], sigma2=sigma2,
+        model_mul=(alpha * np.exp(-SigmaDiag / sigma2))[:, None], gamma=gamma, samples_s=g["pre_samples_s"],
+        sigma2_variance=sv, probability_type=["gauss"], probability_parameters=[g["pre_beta2"]],
+    )
+    assert _relmax(P, g[f"it{it}_out_P"]) < 2e-4
+    assert _relmax(kns, g[f"it{it}_out_K_NA_spatial"]) < 1e-4
+    assert _relmax(kn2, g[f"it{it}_out_K_NA_sigma2"]) < 1e-4
+    assert _relmax(P.sum(1), g[f"it{it}_out_K_NA"]) < 1e-4
+    assert _relmax(P.sum(0), g[f"it{it}_out_K_NB"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_preparation_matches_reference(golden, case):
+    g = golden(case)
+    orc = _make_oracle(g, "float32")
+    assert _relmax(orc.U, g["pre_U"]) < 1e-5
+    assert _relmax(orc.GammaSparse, g["pre_GammaSparse"]) < 1e-5
+    orc.prepare()
+    assert _relmax(orc.coordsA, g["pre_coordsA"]) < 1e-4
+    assert _relmax(orc.coordsB, g["pre_coordsB"]) < 1e-5
+    assert _relmax(orc.sigma2, g["pre_sigma2_0"]) < 1e-4
+    assert _relmax(orc.probability_parameters[0], g["pre_beta2"]) < 1e-4
+    if orc.nn_init:
+        assert orc.inlier_P.shape == g["pre_inlier_P"].shape
+        assert _relmax(orc.init_R, g["pre_init_R"]) < 1e-4
+    if orc.SVI_mode:
+        assert np.array_equal(orc.batch_perm, g["pre_batch_perm"])
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_full_run_matches_reference(golden, case, dtype):
+    g = golden(case)
+    sfx = "" if dtype == "float32" else "_f64"
+    orc = _make_oracle(g, dtype)
+    orc.run()
+    scale = np.abs(g["final_optimal_RnA" + sfx]).max()
+    tol = 2e-4 if dtype == "float32" else 1e-6
+    for key in ("optimal_RnA", "XAHat", "RnA"):
+        assert np.abs(getattr(orc, key) - g[f"final_{key}{sfx}"]).max() / scale < tol, key
+    assert _relmax(orc.sigma2, g["final_sigma2" + sfx]) < 1e-3
+    assert _relmax(orc.gamma, g["final_gamma" + sfx]) < 1e-3
+    assert _relmax(orc.optimal_R, g["final_optimal_R" + sfx]) < tol
+    if "final_P" + sfx in g:
+        num = np.linalg.norm(orc.P.astype(np.float64) - g["final_P" + sfx])
+        assert num / np.linalg.norm(g["final_P" + sfx]) < (2e-2 if dtype == "float32" else 1e-5)
+
+
+def test_ba_transform_reproduces_training_points(golden):
+    g = golden("3d_full_warp")
+    orc = _make_oracle(g, "float64")
+    orc.run()
+    XAHat, _, opt = mo.ba_transform(orc.vecfld, g["raw_coords_moving"], dtype="float64")
+    assert np.abs(XAHat - orc.XAHat).max() < 1e-6 * np.abs(orc.XAHat).max()
+    assert np.abs(opt - orc.optimal_RnA).max() < 1e-6 * np.abs(orc.XAHat).max()
