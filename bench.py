@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py — cell-pairs/sec through the morpho_align EM loop (BASELINE.json metric) on B200.
+
+Workload (default, = BASELINE configs[1]): one synthetic 3-D slice pair per GPU, 100,000 x 100,000 cells, 2,000 genes,
+KL dissimilarity, full EM (SVI_mode=False), K=15 inducing points, nn_init=True, max_iter=200. A *step* is one complete
+200-iteration EM over one slice pair.
+
+  value  = (N_A * N_B * max_iter * n_gpus) / (max-over-ranks device time of one step), cost matrix resident in HBM
+           (EM loop only; preprocess, coarse init, cost precompute and P materialisation excluded).
+  e2e    = the same pairs divided by the time of the public-API path from PINNED HOST buffers: H2D of expression and
+           coordinates, expression-cost precompute, the EM loop, closing similarity and D2H of every result.
+  roofline = E-step sweep kernels: 4 B per cell pair per sweep (algorithmic) / CUDA-event time of each launch, against
+           MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline = the numpy oracle (port of the reference CPU path) on a bounded sample, host cores stated.
+
+``--impl reference`` times the reference's CPU algorithm (oracle port; the reference itself is pure Python and
+/root/reference does not exist on the GPU box) with all host threads on a bounded sample of the same workload.
+Multi-GPU (torchrun): one independent slice pair per rank (weak scaling) + ONE all-gather of the per-pair rigid
+transforms per step for the chain composition.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cells", type=int, default=100000)
+    ap.add_argument("--genes", type=int, default=2000)
+    ap.add_argument("--dim", type=int, default=3)
+    ap.add_argument("--max-iter", type=int, default=200)
+    ap.add_argument("--K", type=int, default=15)
+    ap.add_argument("--svi", action="store_true", help="default SVI mode (batch = N_B/10) instead of the full EM")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-cells", type=int, default=6000, help="cells per slice of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic data generated on the device, staged to pinned host memory
+# ---------------------------------------------------------------------------------------------------------------------
+def make_pair_on_device(n, G, dim, seed, device):
+    import torch
+
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    g = torch.Generator(device=device)
+    g.manual_seed(1234 + seed)
+    coords = torch.rand((n, dim), generator=g, device=device, dtype=torch.float64) * 100
+    if dim == 3:
+        coords[:, 2] *= 0.2  # a 20-unit thick 3-D slab
+    W = torch.randn((dim, G), generator=g, device=device, dtype=torch.float64)
+    phi = torch.rand((G,), generator=g, device=device, dtype=torch.float64) * 2 * np.pi
+
+    def counts(c):
+        lam = torch.exp(torch.sin(c @ W / 30.0 + phi)).float()
+        return torch.poisson(lam, generator=g)
+
+    expA = counts(coords)
+    perm = torch.randperm(n, generator=g, device=device)
+    base = coords[perm]
+    expB = counts(base)
+    th = 0.5
+    R = torch.eye(dim, dtype=torch.float64, device=device)
+    R[0, 0], R[0, 1], R[1, 0], R[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
+    coordsB = base @ R.T + 5.0 + torch.randn((n, dim), generator=g, device=device, dtype=torch.float64) * 0.3
+
+    def pinned(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+
+    hA, hB = pinned(expA), pinned(expB)
+    torch.cuda.synchronize()
+    import pandas as pd
+
+    var = pd.DataFrame(index=[f"g{i}" for i in range(G)])
+    A = AnnDataLite(hA.numpy(), var=var.copy(), obsm={"spatial": coords.cpu().numpy()})
+    B = AnnDataLite(hB.numpy(), var=var.copy(), obsm={"spatial": coordsB.cpu().numpy()})
+    A._pin, B._pin = hA, hB  # keep the pinned storage alive
+    return A, B
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference's numpy path on a bounded sample
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_em_sample(n_cells, G, dim, iters, warm=0, steps=1):
+    """Returns (pairs_per_sec, seconds_per_step, description). EM loop only, cost matrix precomputed (like `value`)."""
+    from oracle.morpho_oracle import MorphoPairOracle
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    (cA, eA), (cB, eB) = make_slice_pair(n_cells, n_cells, G, dim=dim, seed=0, as_anndata=False,
+                                         z_thickness=20.0 if dim == 3 else None)
+    np.random.seed(0)
+    o = MorphoPairOracle(cB, cA, [eB], [eA], dtype="float32", SVI_mode=False, max_iter=iters, K=15, nn_init=False)
+    o.prepare()
+    times = []
+    it = 0
+    for s in range(warm + steps):
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            o.em_iteration(it)
+            it += 1
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times[warm:]))
+    pairs = float(n_cells) * n_cells * iters
+    desc = (f"oracle port of Morpho_pairwise EM (float32 numpy, SVI off, nn_init off), {n_cells}x{n_cells} cells, "
+            f"{G} genes, {dim}-D, {iters} EM iterations per step, cost matrix precomputed")
+    return pairs / sec, sec, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    v, sec, desc = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters, warm=min(args.warmup, 1),
+                                 steps=max(1, min(args.steps, 3)))
+    line = {
+        "impl": "reference",
+        "metric": "cell-pairs/sec through morpho_align EM", "value": v, "unit": "cell-pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": v, "unit": "cell-pairs/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": v, "unit": "cell-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    mode = "SVI(batch=N_B/10)" if args.svi else "full EM (SVI_mode=False)"
+    return {
+        "workload": f"morpho_align pair: 2 synthetic {args.dim}-D slices, {args.cells} cells each, {args.genes} genes, "
+                    f"KL, {mode}, K={args.K}, nn_init=True, max_iter={args.max_iter}; one pair per GPU",
+        "cells_per_slice": args.cells, "genes": args.genes, "dim": args.dim, "max_iter": args.max_iter, "K": args.K,
+        "svi": bool(args.svi), "pairs_per_gpu": 1, "parallelism": "independent slice pair per GPU + 1 all-gather",
+        "cache": "inputs_larger_than_L2 (cost matrix %.1f GB per pair)" % (4.0 * args.cells * args.cells / 1e9),
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import spateo_release_b200 as st
+    from spateo_release_b200 import _capi
+
+    lib = _capi.load_library()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- data + host-side preparation (untimed: preprocessing / coarse init are reported separately) ----
+    t0 = time.perf_counter()
+    A, B = make_pair_on_device(args.cells, args.genes, args.dim, seed=rank, device=dev)
+    t_data = time.perf_counter() - t0
+    np.random.seed(rank)
+    t0 = time.perf_counter()
+    m = st.align.Morpho_pairwise(
+        sampleA=B, sampleB=A, SVI_mode=bool(args.svi), max_iter=args.max_iter, K=args.K, nn_init=True, verbose=False,
+        device=str(local_rank), materialize_P=False, vecfld_key_added="vf",
+    )
+    t_pre = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    m.prepare_host()
+    m.pin_inputs()
+    torch.cuda.synchronize()
+    t_init = time.perf_counter() - t0
+
+    NA, NB = m.NA, m.NB
+    cols = m.batch_size if args.svi else NB
+    pairs_per_step = float(NA) * cols * args.max_iter
+
+    gathered = [torch.zeros(12, dtype=torch.float64, device=dev) for _ in range(world)]
+
+    def consensus_step():
+        """closing similarity of this rank's pair + ONE all-gather + serial chain composition (morpho_alignment.py:300)"""
+        import ctypes as C
+
+        _capi.check(lib.spb_optimal_rigid(C.byref(m._params), _capi.ptr(m._state["optimal"]), _capi.current_stream_ptr()), "opt")
+        if world > 1:
+            dist.all_gather(gathered, m._state["optimal"])
+        else:
+            gathered[0].copy_(m._state["optimal"])
+
+    # ---- end-to-end arm first (public API, pinned host buffers in, numpy results out) ----
+    e2e_times = []
+    h2d = d2h = 0
+    for s in range(1 + max(args.e2e_steps, 1)):
+        m._prepared = False
+        m.__dict__.pop("_GT", None)
+        m.__dict__.pop("_state", None)
+        torch.cuda.empty_cache()
+        m._h2d_bytes = 0
+        barrier()
+        t0 = time.perf_counter()
+        m.prepare_device()          # H2D expression + coords, cost matrix, state
+        m.run_em()
+        consensus_step()
+        m._finish()                 # closing similarity, D2H of coordinates / vectors / scalars
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= 1:
+            e2e_times.append(max_over_ranks(dt))
+        h2d = m._h2d_bytes + (NA + NB) * m.D * 4
+        d2h = NA * m.D * 4 * 3 + NA * 4 * 5 + cols * 4 + 12 * 8 + 264
+        m.SVI_mode = bool(args.svi)
+    e2e_sec = float(np.mean(e2e_times))
+
+    # ---- device-resident arm: EM loop only, cost matrix in HBM ----
+    sampler = ClockSampler(local_rank)
+    step_ms, sweep_ms = [], []
+    launches0 = 0
+    for s in range(args.warmup + args.steps):
+        m.reset_state()
+        ev = []
+        if s == args.warmup:
+            barrier()
+            sampler.start()
+            launches0 = lib.spb_launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        m.run_em(sweep_events=ev)
+        consensus_step()
+        e1.record()
+        barrier()
+        if s >= args.warmup:
+            step_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+            sweep_ms.append([(a.elapsed_time(b), c.elapsed_time(d)) for (a, b, c, d) in ev])
+    launches = lib.spb_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_per_step = float(np.mean(step_ms))
+    value = pairs_per_step * world / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernels (live CUDA-event timings of every launch in the timed region) ----
+    sw = np.array(sweep_ms, dtype=np.float64).reshape(-1, 2)
+    s1_ms, s2_ms = float(sw[:, 0].mean()), float(sw[:, 1].mean())
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 4.0 * NA * cols  # one fp32 g_ij per cell pair per sweep
+    dom_ms = max(s1_ms, s2_ms)
+    roofline = {
+        "bound": "hbm", "kernel": "estep_sweep2_kernel" if s2_ms >= s1_ms else "estep_sweep1_kernel",
+        "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+        "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak_gbs,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+        "traffic": None,
+        "sweep1_ms": s1_ms, "sweep2_ms": s2_ms,
+        "sweep1_GBs": alg_bytes / (s1_ms * 1e-3) / 1e9, "sweep2_GBs": alg_bytes / (s2_ms * 1e-3) / 1e9,
+        "em_loop_GBs_8B_per_pair": 8.0 * pairs_per_step / (ms_per_step * 1e-3) / 1e9,
+        "em_loop_frac": 8.0 * pairs_per_step / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
+        "sweeps_share_of_step": (s1_ms + s2_ms) * args.max_iter / ms_per_step,
+    }
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            v, sec, desc = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters)
+            cpu = {"value": v, "unit": "cell-pairs/s", "cores": os.cpu_count(), "kind": "port", "sample": desc,
+                   "seconds": sec}
+        line = {
+            "metric": "cell-pairs/sec through morpho_align EM", "value": value, "unit": "cell-pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": {"value": pairs_per_step * world / e2e_sec, "unit": "cell-pairs/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_sec, "steps": len(e2e_times),
+                    "includes": "H2D(pinned) of expression+coords, expression-cost precompute, EM loop, closing "
+                                "similarity, all-gather, D2H of results; excludes coarse rigid init / sigma2 / beta2 init"},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "aux": {"datagen_s": t_data, "construct_s": t_pre, "coarse_and_variational_init_s": t_init,
+                    "sigma2_final": float(m.sigma2), "gamma_final": float(m.gamma),
+                    "chain_transforms_gathered": world},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+/*
+ * spateo_b200.h — C ABI of the B200-native morpho-align hot path (libspateo_b200.so).
+ *
+ * The reference (aristoteleo/spateo-release @ 9ce1a90) is pure Python: it has NO FFI for this path. The seam a
+ * maintainer would bind is the array-backend seam `check_backend()/nx.*` (spateo/alignment/methods/utils.py:35-66)
+ * under `Morpho_pairwise` (spateo/alignment/methods/morpho_class.py:54). Every entry point below replaces one math call
+ * site of that class; the citation after each prototype is the reference code it replaces. INTEGRATION.md shows the
+ * ctypes stub that binds them from the reference's side.
+ *
+ * Conventions: plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`; `stream` is a
+ * cudaStream_t passed as void* (NULL = default stream); all functions return 0 on success or a cudaError_t / negative
+ * SPB_E* code, and never synchronise the device unless documented. float = IEEE fp32, accumulators are fp64.
+ *
+ * Layout vocabulary (moving slice A = rows i, fixed slice B = columns j):
+ *   ldx          row pitch: N_A rounded up to SPB_ROW_TILE (1024). Per-row vectors are length ldx.
+ *   xa / XAHat   [3][ldx] structure-of-arrays coordinates (unused dims = 0; pad rows i >= N_A hold 1e18).
+ *   xb4          [N_B][4] fixed-slice coordinates (y0,y1,y2,0).
+ *   GT           [N_B][ldx] expression-probability matrix g_ij stored COLUMN-OF-P-major (one contiguous row per
+ *                fixed cell j; pad entries i >= N_A are 0). 4*N_A*N_B bytes: 40 GB at 100k x 100k.
+ *   UT           [K][ldx] inducing-point kernel U^T.
+ */
+#ifndef SPATEO_B200_H
+#define SPATEO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_ROW_TILE 1024
+#define SPB_COL_STAGE 8
+#define SPB_MAX_K_FUSED 64 /* largest K solved by the in-library Jacobi kernel */
+#define SPB_TRACE_STRIDE 8
+
+#define SPB_EINVAL (-2)
+#define SPB_EUNSUPPORTED (-3)
+
+/* dissimilarity metric / probability type codes (utils.py:900-941, :974-985) */
+#define SPB_METRIC_KL 0
+#define SPB_METRIC_EUC 1 /* "euc"/"euclidean": SQUARED distance (reference quirk) */
+#define SPB_METRIC_COS 2
+#define SPB_METRIC_SQRT_EUC 3 /* "square_euc": sqrt of the squared distance (reference quirk) */
+#define SPB_PROB_GAUSS 0
+#define SPB_PROB_COS 1
+#define SPB_PROB_PROB 2
+
+/* Scalar EM state, resident on the device (doubles; the reference keeps these as fp32 0-d arrays). */
+typedef struct spb_scalars {
+  double sigma2;          /* morpho_class.py:701,1426 */
+  double sigma2_variance; /* annealed spatial variance factor (:705,1431) */
+  double gamma;           /* inlier ratio (:724,1214) */
+  double Sp;              /* (SVI: running average) sum of P (:1171-1185) */
+  double Sp_spatial;
+  double Sp_sigma2;
+  double sigma2_related; /* (:1200) */
+  double step;           /* SVI step size (:894) */
+  double omega;          /* outlier mass of the current E-step (utils.py:1053) */
+  double SpK;            /* un-averaged sum of K_NA of the current batch */
+  double R[9];           /* row-major 3x3 (top-left DxD used) (:1374-1378) */
+  double t[3];           /* (:1398-1402) */
+  double dotKS;          /* sum_i K_NA_sigma2_i * SigmaDiag_i (:1427) */
+  double sums[8];        /* scratch: Sp_spatial_new, Sp_sigma2_new, Sp_new, S2 */
+  float c_q;             /* -log2(e) / (2 sigma2) */
+  float c_s;             /* c_q * sigma2_variance */
+  int32_t nonrigid_flag; /* latched once iter > nonrigid_start_iter (:289-291) */
+  int32_t iter;
+} spb_scalars;
+
+/* Everything one EM iteration touches. One field per line: spateo_release_b200/_capi.py parses this struct. */
+typedef struct spb_em_params {
+  int32_t NA;                  /* moving cells (rows) */
+  int32_t NB;                  /* fixed cells (all columns) */
+  int32_t NBb;                 /* columns per iteration: NB, or the SVI batch size */
+  int32_t D;                   /* 2 or 3 */
+  int32_t K;                   /* inducing points */
+  int32_t ldx;                 /* row pitch (multiple of SPB_ROW_TILE) */
+  int32_t svi;                 /* SVI_mode */
+  int32_t nn_init;             /* coarse-init prior active */
+  int32_t update_R;            /* morpho_class.py:1373 */
+  int32_t nonrigid_start_iter; /* default 80 */
+  int32_t seg1;                /* column segments of sweep 1 */
+  int32_t seg2;                /* column segments of sweep 2 */
+  int32_t nbb_pad;             /* pitch of the column-partial arrays */
+  int32_t trace;               /* 1: record per-iteration scalars into trace_buf */
+  double lambdaVF;
+  double gamma_a;
+  double gamma_b;
+  double samples_s;            /* morpho_class.py:738-741 */
+  double nn_init_weight;
+  double sigma2_variance_decress;
+  double sigma2_variance_end;
+  double inl_SP;               /* sum inlier_P */
+  double inl_Sa[3];            /* inlier_P^T inlier_A */
+  double inl_Sb[3];            /* inlier_P^T inlier_B */
+  double inl_Mab[9];           /* sum_n P_n a_n b_n^T */
+  const float* GT;             /* [NB][ldx] */
+  const float* xa;             /* [3][ldx] rigidly-initialised normalised coords of A (coordsA) */
+  const float* xb4;            /* [NB][4] */
+  const float* UT;             /* [K][ldx] */
+  const float* Gamma;          /* [K][K] GammaSparse */
+  const float* kappa;          /* [ldx] */
+  const int32_t* batch_idx;    /* [max_iter][NBb] SVI column indices per iteration, or NULL */
+  float* alpha;                /* [ldx] */
+  float* SigmaDiag;            /* [ldx] */
+  float* lm;                   /* [ldx] log2(alpha * exp(-SigmaDiag/sigma2)) */
+  float* mm;                   /* [ldx] alpha * exp(-SigmaDiag/sigma2) */
+  float* VnA;                  /* [3][ldx] */
+  float* RnA;                  /* [3][ldx] */
+  float* XAHat;                /* [3][ldx] */
+  float* K_NA;                 /* [ldx] */
+  float* K_NA_spatial;         /* [ldx] */
+  float* K_NA_sigma2;          /* [ldx] */
+  float* PXB;                  /* [3][ldx] rows of P @ XB */
+  float* PXB_term;             /* [3][ldx] (SVI running average) */
+  float* K_NB;                 /* [NBb] */
+  float* colgeom;              /* [nbb_pad][4] coordinates of this iteration's columns */
+  float* colconst;             /* [nbb_pad][8] (y0,y1,y2,a_j, b_j,c_j,0,0) */
+  float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
+  float* rowpart;              /* [seg2][8][ldx] partial row statistics */
+  double* UtWU;                /* [K][K] accumulator */
+  double* UtPXB;               /* [K][3] accumulator */
+  double* SigmaInv;            /* [K][K] (SVI running average) */
+  double* Sigma;               /* [K][K] pinv(SigmaInv) */
+  double* Coff;                /* [K][3] */
+  double* moments;             /* [32] rigid-update moment accumulator */
+  double* jacobi_ws;           /* [2*K*K + 2*K] workspace of the eigen-solver */
+  spb_scalars* sc;             /* device scalars */
+  double* trace_buf;           /* [max_iter][SPB_TRACE_STRIDE] or NULL */
+} spb_em_params;
+
+/* ---- library info ------------------------------------------------------------------------------------------- */
+int spb_version(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t spb_launch_count(void);
+/* sizeof the two structs as compiled (the ctypes mirror checks them at load time) */
+int spb_sizeof_em_params(void);
+int spb_sizeof_scalars(void);
+
+/* ---- expression cost matrix: calc_distance + calc_probability (utils.py:647-788, :866-985) ------------------- */
+/* KL pre-pass: Xn=(X+.01)/rowsum, xlogx=sum Xn log(Xn+1e-8); with is_fixed!=0 writes log(Xn+1e-8) instead. */
+int spb_kl_prepare_rows(const float* X, int64_t n, int64_t G, int64_t ldin, float* out, int64_t ldout, float* rowterm,
+                        int32_t is_fixed, void* stream); /* utils.py:683-695 */
+/* row squared norms (euc) or row-normalisation (cos) */
+int spb_rows_sqnorm(const float* X, int64_t n, int64_t G, int64_t ldin, float* rowterm, void* stream); /* utils.py:780 */
+int spb_rows_normalize(const float* X, int64_t n, int64_t G, int64_t ldin, float* out, int64_t ldout, void* stream); /* utils.py:736-739 */
+/* GT[j][i] (op)= prob(metric(A_i, B_j)); A:[NA][G] pitch lda, B:[NB][G] pitch ldb; accumulate!=0 multiplies into GT */
+int spb_gene_cost(const float* A, int64_t lda, const float* rowtermA, const float* B, int64_t ldb, const float* rowtermB,
+                  int64_t NA, int64_t NB, int64_t G, int32_t metric, int32_t prob_type, float prob_param,
+                  int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:697,780-783,742 + :977-981 */
+/* label layer: GT[j][i] (op)= LT[labA_i][labB_j] */
+int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, int32_t nB_labels, int64_t NA, int64_t NB,
+                   int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:830 */
+
+/* ---- E-step: calc_distance(euc) + get_P_core + row/col sums, P never materialised ---------------------------- */
+int spb_gather_cols(const spb_em_params* p, int32_t iter, void* stream);   /* morpho_class.py:1149 */
+int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1049-1059,1063-1073,1080-1083 (column sums) */
+int spb_col_finalize(const spb_em_params* p, void* stream);               /* utils.py:1053-1055 + denominators */
+int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1059-1083, morpho_class.py:1171-1176,1270,1357 */
+int spb_row_finalize(const spb_em_params* p, void* stream);
+/* dense P [NA][NBb] (row-major, pitch ldp) of the state left by the last E-step */
+int spb_materialize_P(const spb_em_params* p, int32_t iter, float* P, int64_t ldp, void* stream); /* utils.py:1083 */
+
+/* ---- M-step pieces ---------------------------------------------------------------------------------------------- */
+int spb_iter_begin(const spb_em_params* p, int32_t iter, void* stream);      /* morpho_class.py:894 + zeroing */
+int spb_update_gamma_alpha(const spb_em_params* p, void* stream);            /* morpho_class.py:1178-1252 */
+int spb_nonrigid_accumulate(const spb_em_params* p, void* stream);           /* morpho_class.py:1266-1279 */
+int spb_nonrigid_solve(const spb_em_params* p, void* stream);                /* morpho_class.py:1273-1291 (K<=64) */
+int spb_nonrigid_blend(const spb_em_params* p, void* stream);                /* SigmaInv assembly only (K>64 path) */
+int spb_field_apply(const spb_em_params* p, void* stream);                   /* morpho_class.py:1293-1298 */
+int spb_rigid_moments(const spb_em_params* p, void* stream);                 /* morpho_class.py:1312-1318,1356-1357,1427 */
+int spb_rigid_solve(const spb_em_params* p, int32_t iter, void* stream);     /* morpho_class.py:1320-1402,1426-1435 */
+int spb_row_update(const spb_em_params* p, void* stream);                    /* morpho_class.py:1404,293,1087 */
+/* full iteration = all of the above in reference order; needs K <= SPB_MAX_K_FUSED (else call the pieces) */
+int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream);    /* morpho_class.py:280-294 */
+/* closing similarity from the last E-step's statistics: out = optimal_R[9], optimal_t[3] (device doubles) */
+int spb_optimal_rigid(const spb_em_params* p, double* out12, void* stream);  /* morpho_class.py:1451-1468 */
+
+/* ---- Gaussian-kernel vector field ------------------------------------------------------------------------------ */
+/* UT[k][i] = exp(-beta |x_i - z_k|^2);  x:[3][ldx] SoA, z:[K][3] */
+int spb_rbf_kernel_T(const float* x, int64_t n, int64_t ldx, const float* z, int32_t K, float beta, float* UT,
+                     void* stream); /* utils.py:1132-1158 */
+/* out[i][:] = sum_k exp(-beta|q_i - z_k|^2) Coff[k][:] for query points q:[n][D] row-major (fp64 in/out) */
+int spb_field_eval(const double* q, int64_t n, int32_t D, const double* z, const double* Coff, int32_t K, double beta,
+                   double* out, void* stream); /* transform.py:93,103; gaussian_process.py:109,117 */
+
+/* ---- host-buffer convenience (H2D/D2H inside; used for the end-to-end measurement) ------------------------------ */
+int spb_field_eval_host(const double* q_host, int64_t n, int32_t D, const double* z_host, const double* Coff_host,
+                        int32_t K, double beta, double* out_host); /* transform.py:61-116 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPATEO_B200_H */

@@ -1,0 +1,906 @@
+"""``Morpho_pairwise`` — drop-in for ``spateo.alignment.methods.morpho_class.Morpho_pairwise`` (morpho_class.py:54)
+whose EM runs as hand-written sm_100a CUDA kernels behind the C ABI in ``include/spateo_b200.h``.
+
+Host side (this file): validation, gene intersection, dense extraction, coordinate normalisation, inducing-point choice,
+coarse rigid initialisation bookkeeping and output wrapping — same names, argument meaning, RNG call order
+(SURVEY.md Appendix D), result attributes and exceptions as the reference. Device side: expression-cost matrix,
+fused two-sweep E-step (P never materialised), gamma/alpha, non-rigid solve, rigid Procrustes, sigma2; all scalar state
+stays on the device, there is no host synchronisation inside the iteration loop and no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+from .. import _capi
+from .._capi import SpbEmParams, SpbScalars, check, ptr
+from . import utils as U
+
+_METRIC_CODE = {
+    "kl": _capi.CONST["SPB_METRIC_KL"],
+    "euc": _capi.CONST["SPB_METRIC_EUC"],
+    "euclidean": _capi.CONST["SPB_METRIC_EUC"],
+    "square_euc": _capi.CONST["SPB_METRIC_SQRT_EUC"],
+    "square_euclidean": _capi.CONST["SPB_METRIC_SQRT_EUC"],
+    "cos": _capi.CONST["SPB_METRIC_COS"],
+    "cosine": _capi.CONST["SPB_METRIC_COS"],
+}
+_PROB_CODE = {
+    "gauss": _capi.CONST["SPB_PROB_GAUSS"],
+    "gaussian": _capi.CONST["SPB_PROB_GAUSS"],
+    "cos": _capi.CONST["SPB_PROB_COS"],
+    "cosine": _capi.CONST["SPB_PROB_COS"],
+    "prob": _capi.CONST["SPB_PROB_PROB"],
+}
+
+
+def _round_up(x: int, m: int) -> int:
+    return ((x + m - 1) // m) * m
+
+
+def resolve_device(device) -> torch.device:
+    """Reference semantics: "cpu" or a GPU index string (utils.py:35-66). Here every value maps to a CUDA device —
+    there is no CPU path; ``CUDA_VISIBLE_DEVICES`` is NOT mutated (the reference does, utils.py:51)."""
+    _capi.require_cuda()
+    if isinstance(device, torch.device):
+        return device
+    if device is None or device == "cpu" or device == "cuda":
+        return torch.device("cuda", torch.cuda.current_device())
+    if isinstance(device, int):
+        return torch.device("cuda", device)
+    s = str(device)
+    if s.startswith("cuda:"):
+        return torch.device(s)
+    return torch.device("cuda", int(s))
+
+
+class GeneCostBuilder:
+    """Device pipeline for ``calc_distance`` + ``calc_probability`` of one representation layer (utils.py:866-985)."""
+
+    def __init__(self, lib, dev):
+        self.lib, self.dev = lib, dev
+
+    def prepare(self, X: torch.Tensor, metric: str, fixed: bool):
+        """Row pre-pass. Returns (operand [n, Gp] fp32 zero-padded to 16 features, rowterm [n] or None)."""
+        n, G = X.shape
+        Gp = _round_up(G, 16)
+        st = _capi.current_stream_ptr()
+        if metric == "kl":
+            out = torch.empty((n, Gp), dtype=torch.float32, device=self.dev)
+            rt = None if fixed else torch.empty((n,), dtype=torch.float32, device=self.dev)
+            check(self.lib.spb_kl_prepare_rows(ptr(X), n, G, X.stride(0), ptr(out), Gp, ptr(rt), 1 if fixed else 0, st),
+                  "spb_kl_prepare_rows")
+            return out, rt
+        if metric in ("cos", "cosine"):
+            out = torch.empty((n, Gp), dtype=torch.float32, device=self.dev)
+            check(self.lib.spb_rows_normalize(ptr(X), n, G, X.stride(0), ptr(out), Gp, st), "spb_rows_normalize")
+            return out, None
+        # euclidean family: raw values (padded) + squared norms
+        if Gp == G and X.is_contiguous():
+            out = X
+        else:
+            out = torch.zeros((n, Gp), dtype=torch.float32, device=self.dev)
+            out[:, :G] = X
+        rt = torch.empty((n,), dtype=torch.float32, device=self.dev)
+        check(self.lib.spb_rows_sqnorm(ptr(out), n, G, Gp, ptr(rt), st), "spb_rows_sqnorm")
+        return out, rt
+
+    def cost(self, opA, rtA, opB, rtB, NA, NB, G, metric, prob_type, prob_param, accumulate, GT, ldx):
+        check(
+            self.lib.spb_gene_cost(
+                ptr(opA), opA.stride(0), ptr(rtA), ptr(opB), opB.stride(0), ptr(rtB), NA, NB, G, _METRIC_CODE[metric],
+                _PROB_CODE[prob_type], float(prob_param) if prob_param is not None else 1.0, 1 if accumulate else 0,
+                ptr(GT), ldx, _capi.current_stream_ptr(),
+            ),
+            "spb_gene_cost",
+        )
+
+
+class Morpho_pairwise:
+    """Align a moving slice ``sampleA`` onto a fixed slice ``sampleB`` (same constructor as morpho_class.py:110-167).
+
+    Extra keyword (not in the reference): ``materialize_P`` — when False ``run()`` skips building the dense
+    N_A x N_B posterior (40 GB at 100k x 100k) and returns None; every other output is unaffected.
+    Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
+    ``pre_compute_dist``. Not implemented in this round (raise NotImplementedError): ``sparse_calculation_mode``,
+    guidance pairs, ``kernel_type="geodist"``, ``dissimilarity="sym_kl"``.
+    """
+
+    def __init__(
+        self,
+        sampleA,
+        sampleB,
+        rep_layer: Union[str, List[str]] = "X",
+        rep_field: Union[str, List[str]] = "layer",
+        genes=None,
+        spatial_key: str = "spatial",
+        key_added: str = "align_spatial",
+        iter_key_added: Optional[str] = None,
+        save_concrete_iter: bool = False,
+        vecfld_key_added: Optional[str] = None,
+        dissimilarity: Union[str, List[str]] = "kl",
+        probability_type: Union[str, List[str]] = "gauss",
+        probability_parameters=None,
+        label_transfer_dict=None,
+        use_hvg: bool = True,
+        nn_init: bool = True,
+        init_transform: bool = True,
+        allow_flip: bool = False,
+        init_layer: str = "X",
+        init_field: str = "layer",
+        nn_init_top_K: int = 10,
+        nn_init_weight: float = 1.0,
+        max_iter: int = 200,
+        nonrigid_start_iter: int = 80,
+        SVI_mode: bool = True,
+        batch_size: Optional[int] = None,
+        pre_compute_dist: bool = True,
+        sparse_calculation_mode: bool = False,
+        sparse_top_k: int = 1024,
+        lambdaVF: Union[int, float] = 1e2,
+        beta: Union[int, float] = 0.01,
+        K: Union[int, float] = 15,
+        kernel_type: str = "euc",
+        graph=None,
+        graph_knn: int = 10,
+        sigma2_init_scale: Optional[Union[int, float]] = 0.1,
+        sigma2_end: Optional[Union[int, float]] = None,
+        gamma_a: float = 1.0,
+        gamma_b: float = 1.0,
+        kappa: Union[float, np.ndarray] = 1.0,
+        partial_robust_level: float = 10,
+        normalize_c: bool = True,
+        normalize_g: bool = False,
+        separate_mean: bool = True,
+        separate_scale: bool = False,
+        dtype: str = "float32",
+        device: str = "cpu",
+        verbose: bool = True,
+        guidance_pair=None,
+        guidance_effect=False,
+        guidance_weight: float = 1.0,
+        use_chunk: bool = False,
+        chunk_capacity: float = 1.0,
+        return_mapping: bool = False,
+        update_R: bool = True,
+        materialize_P: bool = True,
+    ) -> None:
+        self.verbose = verbose
+        self.sampleA, self.sampleB = sampleA, sampleB
+        self.rep_layer, self.rep_field, self.genes = rep_layer, rep_field, genes
+        self.spatial_key, self.key_added = spatial_key, key_added
+        self.iter_key_added, self.save_concrete_iter = iter_key_added, save_concrete_iter
+        self.vecfld_key_added = vecfld_key_added
+        self.dissimilarity, self.probability_type = dissimilarity, probability_type
+        self.probability_parameters = probability_parameters
+        self.label_transfer_dict = label_transfer_dict
+        self.use_hvg, self.nn_init, self.init_transform = use_hvg, nn_init, init_transform
+        self.nn_init_top_K, self.max_iter, self.allow_flip = nn_init_top_K, max_iter, allow_flip
+        self.init_layer, self.init_field = init_layer, init_field
+        self.SVI_mode, self.batch_size, self.pre_compute_dist = SVI_mode, batch_size, pre_compute_dist
+        self.sparse_calculation_mode, self.sparse_top_k = sparse_calculation_mode, sparse_top_k
+        self.beta, self.lambdaVF, self.K = beta, lambdaVF, int(K)
+        self.kernel_type, self.kernel_bandwidth = kernel_type, beta
+        self.graph, self.graph_knn = graph, graph_knn
+        self.sigma2_init_scale, self.sigma2_end = sigma2_init_scale, sigma2_end
+        self.partial_robust_level = partial_robust_level
+        self.normalize_c, self.normalize_g = normalize_c, normalize_g
+        self.separate_mean, self.separate_scale = separate_mean, separate_scale
+        self.dtype, self.device = dtype, device
+        self.guidance_pair, self.guidance_effect, self.guidance_weight = guidance_pair, guidance_effect, guidance_weight
+        self.use_chunk, self.chunk_capacity = use_chunk, chunk_capacity
+        self.nn_init_weight = nn_init_weight
+        self.gamma_a, self.gamma_b, self.kappa = gamma_a, gamma_b, kappa
+        self.nonrigid_start_iter = nonrigid_start_iter
+        self.return_mapping, self.update_R = return_mapping, update_R
+        self.materialize_P = materialize_P
+
+        self._np_dtype = np.float32 if dtype == "float32" else np.float64
+        self._check()
+        self._lib = _capi.load_library()
+        self._dev = resolve_device(device)
+        with torch.cuda.device(self._dev):
+            self._align_preprocess()
+            self._construct_kernel()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # validation (morpho_class.py:316-440)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _check(self):
+        if self.rep_layer is None:
+            raise ValueError(
+                "No representation input is detected, which may not produce meaningful result. Please check the rep_layer and rep_field."
+            )
+        if self.rep_field is None:
+            self.rep_field = "layer"
+        if isinstance(self.rep_layer, str):
+            self.rep_layer = [self.rep_layer]
+        if isinstance(self.rep_field, str):
+            self.rep_field = [self.rep_field] * len(self.rep_layer)
+        if not U.check_rep_layer([self.sampleA, self.sampleB], self.rep_layer, self.rep_field):
+            raise ValueError("The specified representation is not found in the attribute of the AnnData objects.")
+        self.obs_key = U.check_obs(self.rep_layer, self.rep_field)
+        if self.spatial_key not in self.sampleA.obsm:
+            raise KeyError(f"Spatial key '{self.spatial_key}' not found in sampleA AnnData object.")
+        if self.spatial_key not in self.sampleB.obsm:
+            raise KeyError(f"Spatial key '{self.spatial_key}' not found in sampleB AnnData object.")
+        if self.obs_key is not None and self.label_transfer_dict is not None:
+            catA = self.sampleA.obs[self.obs_key].cat.categories.tolist()
+            catB = self.sampleB.obs[self.obs_key].cat.categories.tolist()
+            U.check_label_transfer_dict(catA, catB, self.label_transfer_dict)
+        if self.dissimilarity is None:
+            self.dissimilarity = "kl"
+        if isinstance(self.dissimilarity, str):
+            self.dissimilarity = [self.dissimilarity] * len(self.rep_layer)
+        valid = ["kl", "sym_kl", "euc", "euclidean", "square_euc", "square_euclidean", "cos", "cosine", "label"]
+        self.dissimilarity = [d.lower() for d in self.dissimilarity]
+        for d in self.dissimilarity:
+            if d not in valid:
+                raise ValueError(f"Invalid `metric` value: {d}. Available `metrics` are: " f"{', '.join(valid)}.")
+        if self.probability_type is None:
+            self.probability_type = "gauss"
+        if isinstance(self.probability_type, str):
+            self.probability_type = [self.probability_type] * len(self.rep_layer)
+        validp = ["gauss", "gaussian", "cos", "cosine", "prob"]
+        self.probability_type = [p.lower() for p in self.probability_type]
+        for p in self.probability_type:
+            if p not in validp:
+                raise ValueError(f"Invalid `metric` value: {p}. Available `metrics` are: " f"{', '.join(validp)}.")
+        for i, f in enumerate(self.rep_field):
+            if f == "obs":
+                self.dissimilarity[i] = "label"
+                self.probability_type[i] = "prob"
+        if self.probability_parameters is None:
+            self.probability_parameters = [None] * len(self.rep_layer)
+        elif not isinstance(self.probability_parameters, (list, tuple)):
+            self.probability_parameters = [self.probability_parameters] * len(self.rep_layer)
+        self.probability_parameters = list(self.probability_parameters)
+        if self.nn_init:
+            if not U.check_rep_layer([self.sampleA, self.sampleB], [self.init_layer], [self.init_field]):
+                raise ValueError("The specified representation is not found in the attribute of the AnnData objects.")
+        if self.guidance_effect:
+            valid_g = ["nonrigid", "rigid", "both"]
+            if self.guidance_effect not in valid_g:
+                raise ValueError(
+                    f"Invalid `guidance_effect` value: {self.guidance_effect}. Available `guidance_effect` values are: "
+                    f"{', '.join(valid_g)}."
+                )
+        # ---- features of the reference that this round does not cover: fail loudly, never silently differ ----
+        if self.sparse_calculation_mode:
+            raise NotImplementedError("sparse_calculation_mode (top-k sparse P) is not implemented in spateo_release_b200 yet.")
+        if (self.guidance_pair is not None) and (self.guidance_effect is not False) and (self.guidance_weight > 0):
+            raise NotImplementedError("guidance_pair is not implemented in spateo_release_b200 yet.")
+        if self.kernel_type != "euc":
+            if self.kernel_type == "geodist":
+                raise NotImplementedError("kernel_type='geodist' is not implemented in spateo_release_b200 yet.")
+            raise NotImplementedError(f"Kernel type '{self.kernel_type}' is not implemented.")
+        if "sym_kl" in self.dissimilarity:
+            raise NotImplementedError("dissimilarity='sym_kl' is not implemented in spateo_release_b200 yet.")
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # preprocessing (morpho_class.py:443-558)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _align_preprocess(self):
+        dt = self._np_dtype
+        if self.use_hvg and ("highly_variable" in self.sampleA.var.columns) and ("highly_variable" in self.sampleB.var.columns):
+            gl = [
+                self.sampleA.var.index[self.sampleA.var.highly_variable],
+                self.sampleB.var.index[self.sampleB.var.highly_variable],
+            ]
+        else:
+            gl = [self.sampleA.var.index, self.sampleB.var.index]
+        common = U.filter_common_genes(*gl, verbose=self.verbose)
+        self.genes = common if self.genes is None else U.intersect_lsts(common, list(self.genes))
+
+        self.exp_layers_A = [U.get_rep(self.sampleA, r, f, self.genes, dt) for r, f in zip(self.rep_layer, self.rep_field)]
+        self.exp_layers_B = [U.get_rep(self.sampleB, r, f, self.genes, dt) for r, f in zip(self.rep_layer, self.rep_field)]
+        if self.obs_key is not None:
+            self.label_transfer = U.check_label_transfer(self.sampleA, self.sampleB, self.obs_key, self.label_transfer_dict)
+        else:
+            self.label_transfer = None
+
+        self.coordsA = U.check_spatial_coords(self.sampleA, self.spatial_key).astype(dt)
+        self.coordsB = U.check_spatial_coords(self.sampleB, self.spatial_key).astype(dt)
+        assert self.coordsA.shape[1] == self.coordsB.shape[1], "Spatial coordinate dimensions are different, please check again."
+        self.NA, self.NB, self.D = self.coordsA.shape[0], self.coordsB.shape[0], self.coordsA.shape[1]
+        if self.normalize_c:
+            self.coordsA, self.coordsB, self.normalize_scales, self.normalize_means = U.normalize_coords(
+                self.coordsA, self.coordsB, self.separate_mean, self.separate_scale
+            )
+        if self.normalize_g:
+            self._normalize_exps()
+        self.guidance = False
+
+    def _normalize_exps(self):
+        """morpho_class.py:657-680: shared RMS scale for 'layer' representations whose metric is not KL."""
+        for i, (f, d) in enumerate(zip(self.rep_field, self.dissimilarity)):
+            if f == "layer" and d != "kl":
+                sc = 0.0
+                for e in (self.exp_layers_A[i], self.exp_layers_B[i]):
+                    sc += np.sqrt(np.sum(e.astype(np.float64) ** 2) / e.shape[0])
+                sc /= 2
+                self.exp_layers_A[i] = (self.exp_layers_A[i] / sc).astype(self._np_dtype)
+                self.exp_layers_B[i] = (self.exp_layers_B[i] / sc).astype(self._np_dtype)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # inducing points + kernel (morpho_class.py:825-875)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _construct_kernel(self):
+        uniq, uniq_idx = np.unique(self.coordsA, return_index=True, axis=0)
+        if uniq.shape[0] > self.K:
+            pick = np.random.choice(uniq.shape[0], self.K, replace=False)
+        else:
+            pick = np.arange(uniq.shape[0])
+        self.inducing_variables_idx = uniq_idx[pick]
+        self.inducing_variables = self.coordsA[self.inducing_variables_idx, :]
+        self.K = self.inducing_variables.shape[0]
+        z = self.inducing_variables.astype(np.float64)
+        d2 = ((z[:, None, :] - z[None, :, :]) ** 2).sum(-1)
+        self.GammaSparse = np.exp(-self.kernel_bandwidth * d2).astype(np.float32)
+        # U^T on the device from the pre-initialisation coordinates (the reference builds U before the coarse init)
+        self.ldx = _round_up(self.NA, _capi.ROW_TILE)
+        dev = self._dev
+        x_soa = torch.zeros((3, self.ldx), dtype=torch.float32, device=dev)
+        x_soa[: self.D, : self.NA] = torch.from_numpy(np.ascontiguousarray(self.coordsA.T, dtype=np.float32)).to(dev)
+        zt = torch.zeros((self.K, 3), dtype=torch.float32, device=dev)
+        zt[:, : self.D] = torch.from_numpy(self.inducing_variables.astype(np.float32)).to(dev)
+        self._UT = torch.empty((self.K, self.ldx), dtype=torch.float32, device=dev)
+        check(
+            self._lib.spb_rbf_kernel_T(ptr(x_soa), self.NA, self.ldx, ptr(zt), self.K, float(self.kernel_bandwidth),
+                                       ptr(self._UT), _capi.current_stream_ptr()),
+            "spb_rbf_kernel_T",
+        )
+
+    @property
+    def U(self) -> np.ndarray:
+        """[N_A, K] kernel matrix as the reference exposes it."""
+        return self._UT[:, : self.NA].T.contiguous().cpu().numpy().astype(self._np_dtype)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # device-side expression distances for small helper problems (coarse init, beta^2 init)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _raw_cost_T(self, XA_host, XB_host, metric):
+        """E^T[j][i] = metric(A_i, B_j) as a device tensor [nB, ldx_s] (columns beyond nA are padding)."""
+        dev = self._dev
+        gc = GeneCostBuilder(self._lib, dev)
+        A = torch.from_numpy(np.ascontiguousarray(XA_host, dtype=np.float32)).to(dev)
+        B = torch.from_numpy(np.ascontiguousarray(XB_host, dtype=np.float32)).to(dev)
+        opA, rtA = gc.prepare(A, metric, fixed=False)
+        opB, rtB = gc.prepare(B, metric, fixed=True)
+        nA, nB, G = A.shape[0], B.shape[0], A.shape[1]
+        lds = _round_up(nA, 128)
+        ET = torch.empty((nB, lds), dtype=torch.float32, device=dev)
+        gc.cost(opA, rtA, opB, rtB, nA, nB, G, metric, "prob", None, False, ET, lds)
+        return ET, nA
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # coarse rigid alignment (morpho_class.py:898-1041): voxelise, mutual top-K by expression, robust Procrustes
+    # ------------------------------------------------------------------------------------------------------------------
+    def _coarse_rigid_alignment(self, n_sampling: int = 20000):
+        top_K = self.nn_init_top_K
+        ia = np.random.choice(self.NA, n_sampling, replace=False) if self.NA > n_sampling else np.arange(self.NA)
+        ib = np.random.choice(self.NB, n_sampling, replace=False) if self.NB > n_sampling else np.arange(self.NB)
+        cA, cB = self.coordsA[ia, :], self.coordsB[ib, :]
+        N, M, D = cA.shape[0], cB.shape[0], cA.shape[1]
+        XA = U.get_rep(self.sampleA[ia], self.init_layer, self.init_field, self.genes, self._np_dtype)
+        XB = U.get_rep(self.sampleB[ib], self.init_layer, self.init_field, self.genes, self._np_dtype)
+        cA, XA = U.voxel_data(cA, XA, voxel_num=max(min(int(N / 20), 1000), 100))
+        cB, XB = U.voxel_data(cB, XB, voxel_num=max(min(int(M / 20), 1000), 100))
+        metric = "kl" if self.init_field == "layer" else "euc"
+        ET, nA = self._raw_cost_T(XA, XB, metric)  # [nB, lds]: ET[b, a] = dist(voxel a of A, voxel b of B)
+        ET = ET[:, :nA]
+        nB = ET.shape[0]
+        while True:
+            try:
+                if top_K > nA - 1 or top_K > nB - 1:  # np.argpartition(kth=top_K) needs kth < size
+                    raise ValueError(f"kth(={top_K}) out of bounds")
+                # for every voxel b of B: the top_K voxels a of A (reference: argpartition over axis 0 of [nA, nB])
+                d1, a_idx = torch.topk(ET, top_K, dim=1, largest=False)
+                NN1 = np.stack([np.repeat(np.arange(nB), top_K), a_idx.reshape(-1).cpu().numpy()], axis=1)
+                dist1 = d1.reshape(-1).cpu().numpy()
+                # for every voxel a of A: the top_K voxels b of B
+                d2, b_idx = torch.topk(ET, top_K, dim=0, largest=False)
+                NN2 = np.stack([b_idx.T.reshape(-1).cpu().numpy(), np.repeat(np.arange(nA), top_K)], axis=1)
+                dist2 = d2.T.reshape(-1).cpu().numpy()
+                break
+            except Exception as e:
+                top_K -= 1
+                if top_K == 0:
+                    raise RuntimeError("Failed to perform coarse rigid alignment after reducing top_K.") from e
+        NN = np.vstack((NN1, NN2))
+        distance = np.r_[dist1, dist2].astype(np.float64)
+        train_x, train_y = cA[NN[:, 1], :], cB[NN[:, 0], :]
+        P, R, t, _, sigma2, gamma = U.inlier_from_NN(train_x, train_y, distance[:, None])
+        if self.allow_flip:
+            Rf = np.eye(D)
+            Rf[-1, -1] = -1
+            P2, R2, t2, _, s2, g2 = U.inlier_from_NN(train_x @ Rf, train_y, distance[:, None])
+            if g2 > gamma:
+                P, R, t, sigma2 = P2, R2 @ Rf, t2, s2
+        thr = min(P[np.argsort(-P[:, 0])[20], 0], 0.5)
+        keep = np.where(P[:, 0] > thr)[0]
+        dt = self._np_dtype
+        self.inlier_A = train_x[keep, :].astype(dt)
+        self.inlier_B = train_y[keep, :].astype(dt)
+        self.inlier_P = P[keep, :].astype(dt)
+        self.init_R = R.astype(dt)
+        self.init_t = np.asarray(t).astype(dt)
+        if self.init_transform:
+            self.inlier_A = self.inlier_A @ self.init_R.T + self.init_t
+            self.coordsA = self.coordsA @ self.init_R.T + self.init_t
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # variational initialisation (morpho_class.py:683-820; utils.py:1339-1354)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _init_guess_sigma2(self, subsample: int = 20000) -> float:
+        NA, NB, D = self.NA, self.NB, self.D
+        sa = np.random.choice(NA, subsample, replace=False) if NA > subsample else np.arange(NA)
+        sb = np.random.choice(NB, subsample, replace=False) if NB > subsample else np.arange(NB)
+        xa = torch.from_numpy(self.coordsA[sa].astype(np.float64)).to(self._dev)
+        xb = torch.from_numpy(self.coordsB[sb].astype(np.float64)).to(self._dev)
+        total = torch.zeros((), dtype=torch.float64, device=self._dev)
+        for c in range(0, xa.shape[0], 4096):
+            d2 = torch.cdist(xa[c : c + 4096], xb) ** 2
+            total += (d2 * d2).sum()  # the reference squares the already squared distance (utils.py:1352)
+        return float(total.item()) / (D * sa.shape[0] * sa.shape[0])
+
+    def _init_probability_parameters(self, subsample: int = 20000):
+        for i, (eA, eB, d_s, p_t, p_p) in enumerate(
+            zip(self.exp_layers_A, self.exp_layers_B, self.dissimilarity, self.probability_type, self.probability_parameters)
+        ):
+            if p_p is not None or p_t.lower() not in ("gauss", "gaussian"):
+                continue
+            sa = np.random.choice(self.NA, subsample, replace=False) if self.NA > subsample else np.arange(self.NA)
+            sb = np.random.choice(self.NB, subsample, replace=False) if self.NB > subsample else np.arange(self.NB)
+            ET, nA = self._raw_cost_T(eA[sa], eB[sb], d_s)
+            mn = ET[:, :nA].min(dim=0).values  # min over fixed cells for every moving cell (utils: nx.min(exp_dist, 1))
+            srt = torch.sort(mn).values
+            val = float(srt[int(sa.shape[0] * 0.05)].item()) / 5
+            self.probability_parameters[i] = np.maximum(np.asarray(val, dtype=self._np_dtype), np.asarray(0.01, dtype=self._np_dtype))
+            del ET
+
+    def _initialize_variational_variables(self):
+        dt = self._np_dtype
+        self.sigma2 = np.asarray(self.sigma2_init_scale * self._init_guess_sigma2(), dtype=dt)
+        self._sigma2_init = float(self.sigma2)
+        self._init_probability_parameters()
+        self.sigma2_variance = 1.0
+        self.sigma2_variance_end = float(self.partial_robust_level)
+        self.sigma2_variance_decress = float(np.power(np.asarray(self.sigma2_variance_end / self.sigma2_variance, dtype=dt), 1 / 100))
+        if isinstance(self.kappa, float):
+            self.kappa = np.ones((self.NA,), dtype=dt) * self.kappa
+        elif isinstance(self.kappa, np.ndarray):
+            self.kappa = self.kappa.astype(dt)
+        else:
+            raise ValueError("kappa should be a float or a numpy array.")
+        self.gamma = np.asarray(0.5, dtype=dt)
+        self.samples_s = float(
+            np.maximum(
+                np.prod(self.coordsA.max(axis=0) - self.coordsA.min(axis=0)),
+                np.prod(self.coordsB.max(axis=0) - self.coordsB.min(axis=0)),
+            )
+        )
+        self.outlier_s = self.samples_s * self.NA
+        self.nonrigid_flag = False
+        if self.SVI_mode:
+            if self.batch_size is None:
+                self.batch_size = min(max(int(self.NB / 10), 1000), self.NB)
+            else:
+                self.batch_size = min(self.batch_size, self.NB)
+            self.batch_perm = np.random.permutation(self.NB)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # device state
+    # ------------------------------------------------------------------------------------------------------------------
+    def _build_gene_cost(self):
+        """GT[j][i] = prod_layers prob(metric(A_i, B_j)) (morpho_class.py:265-268 + utils.py:1080-1081)."""
+        dev, lib = self._dev, self._lib
+        self._GT = torch.empty((self.NB, self.ldx), dtype=torch.float32, device=dev)
+        gc = GeneCostBuilder(lib, dev)
+        first = True
+        for eA, eB, d_s, p_t, p_p in zip(
+            self.exp_layers_A, self.exp_layers_B, self.dissimilarity, self.probability_type, self.probability_parameters
+        ):
+            if d_s == "label":
+                la = torch.from_numpy(np.ascontiguousarray(eA, dtype=np.int32)).to(dev)
+                lb = torch.from_numpy(np.ascontiguousarray(eB, dtype=np.int32)).to(dev)
+                LT = torch.from_numpy(np.ascontiguousarray(self.label_transfer, dtype=np.float32)).to(dev)
+                check(
+                    lib.spb_label_cost(ptr(la), ptr(lb), ptr(LT), LT.shape[1], self.NA, self.NB, 0 if first else 1,
+                                       ptr(self._GT), self.ldx, _capi.current_stream_ptr()),
+                    "spb_label_cost",
+                )
+            else:
+                A = self._to_device_pinned(eA)
+                B = self._to_device_pinned(eB)
+                opA, rtA = gc.prepare(A, d_s, fixed=False)
+                opB, rtB = gc.prepare(B, d_s, fixed=True)
+                gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, eA.shape[1], d_s, p_t, p_p, not first, self._GT, self.ldx)
+                del A, B, opA, opB
+            first = False
+
+    def _to_device_pinned(self, host_array: np.ndarray) -> torch.Tensor:
+        """Host -> device copy of one dense representation; the host side is staged in pinned memory once."""
+        key = id(host_array)
+        cache = self.__dict__.setdefault("_pinned", {})
+        if key not in cache:
+            t = torch.from_numpy(np.ascontiguousarray(host_array, dtype=np.float32))
+            cache[key] = t if t.is_pinned() else t.pin_memory()
+        self._h2d_bytes = getattr(self, "_h2d_bytes", 0) + cache[key].numel() * 4
+        return cache[key].to(self._dev, non_blocking=True)
+
+    def pin_inputs(self):
+        """Stage the dense representations in pinned host memory ahead of time (part of preprocessing)."""
+        for e in list(self.exp_layers_A) + list(self.exp_layers_B):
+            if e.dtype.kind == "f":
+                key = id(e)
+                cache = self.__dict__.setdefault("_pinned", {})
+                if key not in cache:
+                    t = torch.from_numpy(np.ascontiguousarray(e, dtype=np.float32))
+                    cache[key] = t if t.is_pinned() else t.pin_memory()
+
+    @staticmethod
+    def _choose_segments(nrb: int, nbb: int) -> int:
+        """Column segments so that CTAs ~ a multiple of 2 x 148 and a segment is at most ~4096 columns."""
+        max_seg = max(1, nbb // _capi.COL_STAGE)
+        seg = 1
+        for waves in range(1, 64):
+            seg = max(1, min(max_seg, (296 * waves) // max(nrb, 1)))
+            if (nbb + seg - 1) // seg <= 4096 or seg == max_seg:
+                break
+        return seg
+
+    def _allocate_state(self):
+        dev, D, NA, NB, K, ldx = self._dev, self.D, self.NA, self.NB, self.K, self.ldx
+        f32, f64 = torch.float32, torch.float64
+        nbb = self.batch_size if self.SVI_mode else NB
+        nbb_alloc = NB if (self.return_mapping and self.SVI_mode) else nbb
+        self._NBb = nbb
+        nrb = ldx // _capi.ROW_TILE
+        self._nbb_pad = _round_up(nbb_alloc, 8) + 8
+        s = {}
+        s["xa"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["xa"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(self.coordsA.T, dtype=np.float32)).to(dev)
+        s["xb4"] = torch.zeros((NB, 4), dtype=f32, device=dev)
+        s["xb4"][:, :D] = torch.from_numpy(self.coordsB.astype(np.float32)).to(dev)
+        s["Gamma"] = torch.from_numpy(np.ascontiguousarray(self.GammaSparse, dtype=np.float32)).to(dev)
+        s["kappa"] = torch.ones((ldx,), dtype=f32, device=dev)
+        s["kappa"][:NA] = torch.from_numpy(self.kappa.astype(np.float32)).to(dev)
+        s["alpha"] = torch.ones((ldx,), dtype=f32, device=dev)
+        s["SigmaDiag"] = torch.zeros((ldx,), dtype=f32, device=dev)
+        s["lm"] = torch.zeros((ldx,), dtype=f32, device=dev)
+        s["mm"] = torch.zeros((ldx,), dtype=f32, device=dev)
+        s["VnA"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["RnA"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["XAHat"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["XAHat"][:, NA:] = 1e18  # pad rows sit infinitely far from every fixed cell
+        for k in ("K_NA", "K_NA_spatial", "K_NA_sigma2"):
+            s[k] = torch.zeros((ldx,), dtype=f32, device=dev)
+        s["PXB"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["PXB_term"] = torch.zeros((3, ldx), dtype=f32, device=dev)
+        s["K_NB"] = torch.zeros((self._nbb_pad,), dtype=f32, device=dev)
+        s["colgeom"] = torch.zeros((self._nbb_pad, 4), dtype=f32, device=dev)
+        s["colconst"] = torch.zeros((self._nbb_pad, 8), dtype=f32, device=dev)
+        s["colpart"] = torch.zeros((nrb, 4, self._nbb_pad), dtype=f32, device=dev)
+        seg1 = self._choose_segments(nrb, nbb)
+        seg2 = self._choose_segments(nrb, nbb)
+        seg_alloc = max(seg2, self._choose_segments(nrb, nbb_alloc))
+        s["rowpart"] = torch.zeros((seg_alloc, 8, ldx), dtype=f32, device=dev)
+        s["UtWU"] = torch.zeros((K, K), dtype=f64, device=dev)
+        s["UtPXB"] = torch.zeros((K, 3), dtype=f64, device=dev)
+        s["SigmaInv"] = torch.zeros((K, K), dtype=f64, device=dev)
+        s["Sigma"] = torch.zeros((K, K), dtype=f64, device=dev)
+        s["Coff"] = torch.zeros((K, 3), dtype=f64, device=dev)
+        s["moments"] = torch.zeros((32,), dtype=f64, device=dev)
+        s["trace_buf"] = torch.zeros((max(self.max_iter, 1), _capi.TRACE_STRIDE), dtype=f64, device=dev)
+        s["optimal"] = torch.zeros((12,), dtype=f64, device=dev)
+        if self.SVI_mode:
+            # the whole batch schedule is a deterministic function of the initial permutation (morpho_class.py:894-896)
+            sched = np.empty((max(self.max_iter, 1), nbb), dtype=np.int32)
+            perm = self.batch_perm.copy()
+            for it in range(self.max_iter):
+                sched[it] = perm[:nbb]
+                perm = np.roll(perm, nbb)
+            self.batch_idx = sched[self.max_iter - 1].astype(np.int64) if self.max_iter > 0 else None
+            s["batch_idx"] = torch.from_numpy(sched).to(dev)
+        else:
+            s["batch_idx"] = None
+        # scalars
+        sc = SpbScalars()
+        sc.sigma2 = float(self._sigma2_init)
+        sc.sigma2_variance = 1.0
+        sc.gamma = 0.5
+        for q in range(9):
+            sc.R[q] = 1.0 if q in (0, 4, 8) else 0.0
+        host_sc = np.frombuffer(bytes(sc), dtype=np.uint8).copy()
+        s["sc"] = torch.from_numpy(host_sc).to(dev)
+        self._state = s
+        # params
+        p = SpbEmParams()
+        p.NA, p.NB, p.NBb, p.D, p.K, p.ldx = NA, NB, nbb, D, K, ldx
+        p.svi, p.nn_init, p.update_R = int(self.SVI_mode), int(self.nn_init), int(self.update_R)
+        p.nonrigid_start_iter = int(self.nonrigid_start_iter)
+        p.seg1, p.seg2, p.nbb_pad, p.trace = seg1, seg2, self._nbb_pad, 1
+        p.lambdaVF, p.gamma_a, p.gamma_b = float(self.lambdaVF), float(self.gamma_a), float(self.gamma_b)
+        p.samples_s = float(self.samples_s)
+        p.nn_init_weight = float(self.nn_init_weight)
+        p.sigma2_variance_decress = float(self.sigma2_variance_decress)
+        p.sigma2_variance_end = float(self.sigma2_variance_end)
+        if self.nn_init:
+            Pn = self.inlier_P.astype(np.float64)[:, 0]
+            a = np.zeros((Pn.shape[0], 3))
+            b = np.zeros((Pn.shape[0], 3))
+            a[:, :D] = self.inlier_A.astype(np.float64)
+            b[:, :D] = self.inlier_B.astype(np.float64)
+            p.inl_SP = float(Pn.sum())
+            Sa, Sb = Pn @ a, Pn @ b
+            Mab = (a * Pn[:, None]).T @ b
+            for d in range(3):
+                p.inl_Sa[d], p.inl_Sb[d] = float(Sa[d]), float(Sb[d])
+            for q in range(9):
+                p.inl_Mab[q] = float(Mab.reshape(-1)[q])
+        else:
+            p.inl_SP = 1.0
+        p.GT, p.UT = ptr(self._GT).value, ptr(self._UT).value
+        for name in ("xa", "xb4", "Gamma", "kappa", "batch_idx", "alpha", "SigmaDiag", "lm", "mm", "VnA", "RnA", "XAHat",
+                     "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart",
+                     "rowpart", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc", "trace_buf"):
+            t = s[name]
+            setattr(p, name, None if t is None else t.data_ptr())
+        p.jacobi_ws = None
+        self._params = p
+
+    def _read_scalars(self) -> SpbScalars:
+        raw = self._state["sc"].cpu().numpy().tobytes()
+        return SpbScalars.from_buffer_copy(raw)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # the EM loop
+    # ------------------------------------------------------------------------------------------------------------------
+    def _nonrigid_solve_large_K(self, st):
+        """K > SPB_MAX_K_FUSED: eigen pseudo-inverse through cuSOLVER (torch.linalg.eigh, fp64), same cutoff rule."""
+        lib, p, s = self._lib, self._params, self._state
+        check(lib.spb_nonrigid_blend(C.byref(p), st), "spb_nonrigid_blend")
+        A = s["SigmaInv"]
+        A = 0.5 * (A + A.T)
+        ev, V = torch.linalg.eigh(A)
+        cutoff = ev.abs().max() * self.K * 1.1920928955078125e-07
+        inv = torch.where(ev.abs() > cutoff, 1.0 / ev, torch.zeros_like(ev))
+        Sigma = (V * inv) @ V.T
+        s["Sigma"].copy_(Sigma)
+        s["Coff"].copy_(Sigma @ s["UtPXB"])
+
+    def _iteration(self, it: int, st, capture_P: bool = False, sweep_events: Optional[list] = None):
+        """One EM iteration (morpho_class.py:280-294). The fused C entry point is used unless the iteration has to be
+        split: K > SPB_MAX_K_FUSED (eigen solve through cuSOLVER) or ``capture_P`` (dense P of THIS E-step, which must
+        be written before the M-step moves the cells)."""
+        lib, p = self._lib, self._params
+        nonrigid = it > self.nonrigid_start_iter
+        large_K = nonrigid and self.K > _capi.MAX_K_FUSED
+        if not (large_K or capture_P or sweep_events is not None):
+            check(lib.spb_em_iteration(C.byref(p), it, st), "spb_em_iteration")
+            return
+        self._estep_only(it, st, sweep_events)
+        if capture_P:
+            self._P_dev = torch.empty((self.NA, self._NBb), dtype=torch.float32, device=self._dev)
+            check(lib.spb_materialize_P(C.byref(p), it, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
+        check(lib.spb_update_gamma_alpha(C.byref(p), st), "spb_update_gamma_alpha")
+        if nonrigid:
+            check(lib.spb_nonrigid_accumulate(C.byref(p), st), "spb_nonrigid_accumulate")
+            if large_K:
+                self._nonrigid_solve_large_K(st)
+            else:
+                check(lib.spb_nonrigid_solve(C.byref(p), st), "spb_nonrigid_solve")
+            check(lib.spb_field_apply(C.byref(p), st), "spb_field_apply")
+        check(lib.spb_rigid_moments(C.byref(p), st), "spb_rigid_moments")
+        check(lib.spb_rigid_solve(C.byref(p), it, st), "spb_rigid_solve")
+        check(lib.spb_row_update(C.byref(p), st), "spb_row_update")
+
+    def _estep_only(self, it: int, st, sweep_events: Optional[list] = None):
+        """One E-step + the statistics the closing similarity needs (used for return_mapping under SVI)."""
+        lib, p = self._lib, self._params
+        check(lib.spb_iter_begin(C.byref(p), it, st), "spb_iter_begin")
+        check(lib.spb_gather_cols(C.byref(p), it, st), "spb_gather_cols")
+        if sweep_events is not None:
+            e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+            e0.record()
+        check(lib.spb_estep_sweep1(C.byref(p), it, st), "spb_estep_sweep1")
+        if sweep_events is not None:
+            e1.record()
+        check(lib.spb_col_finalize(C.byref(p), st), "spb_col_finalize")
+        if sweep_events is not None:
+            e2.record()
+        check(lib.spb_estep_sweep2(C.byref(p), it, st), "spb_estep_sweep2")
+        if sweep_events is not None:
+            e3.record()
+            sweep_events.append((e0, e1, e2, e3))
+        check(lib.spb_row_finalize(C.byref(p), st), "spb_row_finalize")
+
+    def prepare_host(self):
+        """Coarse rigid initialisation + variational initialisation (host numpy with small device helpers); consumes
+        the global ``np.random`` stream in the reference's order (morpho_class.py:258-261)."""
+        with torch.cuda.device(self._dev):
+            if self.nn_init:
+                self._coarse_rigid_alignment()
+            self._initialize_variational_variables()
+        self._host_ready = True
+
+    def prepare_device(self):
+        """Host -> device copies of the inputs, expression-cost matrix, EM state (morpho_class.py:265-268)."""
+        if not getattr(self, "_host_ready", False):
+            self.prepare_host()
+        with torch.cuda.device(self._dev):
+            self._build_gene_cost()
+            self._allocate_state()
+            check(self._lib.spb_row_update(C.byref(self._params), _capi.current_stream_ptr()), "spb_row_update")
+        self._prepared = True
+
+    def prepare(self):
+        """Everything ``run`` does before the loop: coarse init, variational init, cost matrix, device state."""
+        self.prepare_host()
+        self.prepare_device()
+
+    def reset_state(self):
+        """Rewind the EM state to iteration 0 (benchmark repetitions); the cost matrix stays resident."""
+        with torch.cuda.device(self._dev):
+            self._allocate_state()
+            check(self._lib.spb_row_update(C.byref(self._params), _capi.current_stream_ptr()), "spb_row_update")
+
+    def run_em(self, n_iter: Optional[int] = None, start: int = 0, sweep_events: Optional[list] = None):
+        """Enqueue EM iterations [start, start + n_iter) on the current stream (no host synchronisation).
+
+        ``sweep_events``: optional list that receives (start, mid, end) CUDA events recorded around the two E-step sweep
+        kernels of every iteration on the launching stream (bench.py's live roofline measurement)."""
+        n_iter = self.max_iter - start if n_iter is None else n_iter
+        with torch.cuda.device(self._dev):
+            st = _capi.current_stream_ptr()
+            hist = self._state.get("hist")
+            for it in range(start, start + n_iter):
+                if hist is not None:
+                    hist[it].copy_(self._state["XAHat"])
+                    self._state["hist_sigma2"][it].copy_(self._state["sc"][:8].view(torch.float64)[0])
+                last = it == self.max_iter - 1
+                want_P = self.materialize_P and last and not (self.return_mapping and self.SVI_mode)
+                self._iteration(it, st, capture_P=want_P, sweep_events=sweep_events)
+
+    @torch.no_grad()
+    def run(self):
+        """morpho_class.py:242-313. Returns P [N_A, N_B | batch] (numpy) or None when ``materialize_P=False``."""
+        if not getattr(self, "_prepared", False):
+            self.prepare_device()
+        with torch.cuda.device(self._dev):
+            if self.iter_key_added is not None:
+                self._state["hist"] = torch.empty((max(self.max_iter, 1), 3, self.ldx), dtype=torch.float32, device=self._dev)
+                self._state["hist_sigma2"] = torch.zeros((max(self.max_iter, 1),), dtype=torch.float64, device=self._dev)
+            self.run_em()
+            self._finish()
+        return self.P
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # closing similarity + output wrapping (morpho_class.py:296-313, 1437-1528)
+    # ------------------------------------------------------------------------------------------------------------------
+    def _finish(self):
+        lib, p, s = self._lib, self._params, self._state
+        st = _capi.current_stream_ptr()
+        dt = self._np_dtype
+        D, NA = self.D, self.NA
+        last_iter = max(self.max_iter - 1, 0)
+        if self.sigma2_end is not None:
+            sc = self._read_scalars()
+            sc.sigma2 = float(self.sigma2_end)
+            s["sc"].copy_(torch.from_numpy(np.frombuffer(bytes(sc), dtype=np.uint8).copy()))
+            check(lib.spb_row_update(C.byref(p), st), "spb_row_update")
+        if self.max_iter == 0:
+            self._estep_only(0, st)
+            check(lib.spb_rigid_moments(C.byref(p), st), "spb_rigid_moments")
+        if self.return_mapping and self.SVI_mode:
+            # full (non-SVI) posterior with the final parameters (morpho_class.py:300-302)
+            self.SVI_mode = False
+            p.svi, p.NBb = 0, self.NB
+            p.seg1 = p.seg2 = self._choose_segments(self.ldx // _capi.ROW_TILE, self.NB)
+            self._NBb = self.NB
+            self._estep_only(last_iter, st)
+            # scalar Sp's must become the un-averaged sums (morpho_class.py:1183-1185)
+            sc = self._read_scalars()
+            sc.Sp_spatial, sc.Sp_sigma2, sc.Sp = sc.sums[0], sc.sums[1], sc.sums[2]
+            s["sc"].copy_(torch.from_numpy(np.frombuffer(bytes(sc), dtype=np.uint8).copy()))
+            s["moments"].zero_()
+            check(lib.spb_rigid_moments(C.byref(p), st), "spb_rigid_moments")
+        check(lib.spb_optimal_rigid(C.byref(p), ptr(s["optimal"]), st), "spb_optimal_rigid")
+        opt = s["optimal"].cpu().numpy()
+        sc = self._read_scalars()
+        R3 = np.array(list(sc.R), dtype=np.float64).reshape(3, 3)
+        self.R = R3[:D, :D].astype(dt)
+        self.t = np.array(list(sc.t), dtype=np.float64)[None, :D].astype(dt)
+        self.optimal_R = opt[:9].reshape(3, 3)[:D, :D].astype(dt)
+        self.optimal_t = opt[9 : 9 + D].astype(dt)
+        self.sigma2 = np.asarray(sc.sigma2, dtype=dt)
+        self.gamma = np.asarray(sc.gamma, dtype=dt)
+        self.sigma2_variance = np.asarray(sc.sigma2_variance, dtype=dt)
+        self.Sp, self.Sp_spatial, self.Sp_sigma2 = sc.Sp, sc.Sp_spatial, sc.Sp_sigma2
+        self.nonrigid_flag = self.max_iter - 1 > self.nonrigid_start_iter
+
+        def rows(name):  # [3, ldx] SoA -> [NA, D]
+            return s[name][:D, :NA].T.contiguous().cpu().numpy().astype(dt)
+
+        self.XAHat, self.RnA, self.VnA = rows("XAHat"), rows("RnA"), rows("VnA")
+        self.optimal_RnA = (self.coordsA.astype(np.float64) @ self.optimal_R.astype(np.float64).T + self.optimal_t).astype(dt)
+        self.K_NA = s["K_NA"][:NA].cpu().numpy().astype(dt)
+        self.K_NB = s["K_NB"][: self._NBb].cpu().numpy().astype(dt)
+        self.K_NA_spatial = s["K_NA_spatial"][:NA].cpu().numpy().astype(dt)
+        self.K_NA_sigma2 = s["K_NA_sigma2"][:NA].cpu().numpy().astype(dt)
+        self.alpha = s["alpha"][:NA].cpu().numpy().astype(dt)
+        self.SigmaDiag = s["SigmaDiag"][:NA].cpu().numpy().astype(dt)
+        if self.nonrigid_flag:
+            self.Coff = s["Coff"][:, :D].cpu().numpy().astype(dt)
+            self.SigmaInv = s["SigmaInv"].cpu().numpy().astype(dt)
+        else:
+            self.Coff = np.zeros(self.K, dtype=dt)  # the reference's initial value (morpho_class.py:733)
+        self.trace = s["trace_buf"].cpu().numpy()
+        if self.materialize_P:
+            if getattr(self, "_P_dev", None) is None:  # max_iter == 0 or the return_mapping E-step above
+                self._P_dev = torch.empty((NA, self._NBb), dtype=torch.float32, device=self._dev)
+                check(lib.spb_materialize_P(C.byref(p), last_iter, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
+            self.P = self._P_dev.cpu().numpy().astype(dt)
+            self._P_dev = None
+        else:
+            self.P = None
+        if self.iter_key_added is not None:
+            hist = s["hist"][:, :D, :NA].permute(0, 2, 1).contiguous().cpu().numpy().astype(dt)
+            sig = s["hist_sigma2"].cpu().numpy()
+            self.iter_added = {self.key_added: {}, "sigma2": {}}
+            for it in range(self.max_iter):
+                xa = hist[it]
+                if self.normalize_c:
+                    xa = xa * self.normalize_scales[1] + self.normalize_means[1]
+                self.iter_added[self.key_added][it] = xa
+                self.iter_added["sigma2"][it] = np.asarray(sig[it], dtype=dt)
+        self._wrap_output()
+
+    def _wrap_output(self):
+        if self.normalize_c:
+            sc1, m1 = self.normalize_scales[1], self.normalize_means[1]
+            self.XAHat = self.XAHat * sc1 + m1
+            self.RnA = self.RnA * sc1 + m1
+            self.optimal_RnA = self.optimal_RnA * sc1 + m1
+        if self.vecfld_key_added is not None:
+            norm_dict = {
+                "mean_transformed": self.normalize_means[0],
+                "mean_fixed": self.normalize_means[1],
+                "scale": self.normalize_scales[0],
+                "scale_transformed": self.normalize_scales[0],
+                "scale_fixed": self.normalize_scales[1],
+            } if self.normalize_c else None
+            self.vecfld = {
+                "R": self.R,
+                "t": self.t,
+                "optimal_R": self.optimal_R,
+                "optimal_t": self.optimal_t,
+                "init_R": self.init_R if self.nn_init else np.eye(self.D),
+                "init_t": self.init_t if self.nn_init else np.zeros(self.D),
+                "beta": self.beta,
+                "Coff": self.Coff,
+                "inducing_variables": self.inducing_variables,
+                "normalize_scales": self.normalize_scales if self.normalize_c else None,
+                "normalize_means": self.normalize_means if self.normalize_c else None,
+                "normalize_c": self.normalize_c,
+                "dissimilarity": self.dissimilarity,
+                "sigma2": self.sigma2,
+                "gamma": self.gamma,
+                "NA": self.NA,
+                "sigma2_variance": self.sigma2_variance,
+                "method": "Spateo",
+                "norm_dict": norm_dict,
+                "kernel_type": self.kernel_type,
+            }
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # test / debugging access to the device state
+    # ------------------------------------------------------------------------------------------------------------------
+    def device_vector(self, name: str) -> np.ndarray:
+        t = self._state[name]
+        return t.cpu().numpy()

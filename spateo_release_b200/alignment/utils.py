@@ -1,0 +1,283 @@
+"""Host-side helpers of the alignment path (validation, dense extraction, normalisation, coarse-init pieces).
+
+These mirror the *behaviour* (names, argument meaning, exceptions) of ``spateo/alignment/methods/utils.py`` and
+``spateo/alignment/utils.py`` for the functions the pairwise solver calls; the heavy array math lives in the CUDA library.
+All ``file:line`` citations are relative to the reference tree.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import pandas as pd
+from scipy.sparse import issparse
+from scipy.spatial import cKDTree
+
+
+def intersect_lsts(*lsts):
+    """Intersection of lists, keeping the order of the first list (reference: unordered set, utils.py:21)."""
+    others = [set(l) for l in lsts[1:]]
+    return [g for g in lsts[0] if all(g in o for o in others)]
+
+
+def filter_common_genes(*genes, verbose: bool = True) -> list:
+    """utils.py:494-512 — raises ValueError when the samples share no gene."""
+    common = intersect_lsts(*[list(g) for g in genes])
+    if len(common) == 0:
+        raise ValueError("The number of common gene between all samples is 0.")
+    return common
+
+
+def to_dense_matrix(X):
+    return X.toarray() if issparse(X) else np.array(X)
+
+
+def check_spatial_coords(sample, spatial_key: str = "spatial") -> np.ndarray:
+    """utils.py:70-108 — returns the coordinates without constant axes; must end up 2-D or 3-D."""
+    if spatial_key not in sample.obsm:
+        raise KeyError(f"Spatial key '{spatial_key}' not found in AnnData object.")
+    coordinates = sample.obsm[spatial_key].copy()
+    if isinstance(coordinates, pd.DataFrame):
+        coordinates = coordinates.values
+    coordinates = np.asarray(coordinates)
+    keep = [i for i in range(coordinates.shape[1]) if len(np.unique(coordinates[:, i])) != 1]
+    coordinates = coordinates[:, keep]
+    if coordinates.shape[1] > 3 or coordinates.shape[1] < 2:
+        raise ValueError(f"The spatial coordinate '{spatial_key}' should only has 2 / 3 dimension")
+    return np.ascontiguousarray(coordinates)
+
+
+def check_exp(sample, layer: str = "X") -> np.ndarray:
+    """utils.py:112-135 — dense expression matrix of ``.X`` or ``.layers[layer]``."""
+    if layer == "X":
+        m = sample.X.copy()
+    else:
+        if layer not in sample.layers:
+            raise KeyError(f"Layer '{layer}' not found in AnnData object.")
+        m = sample.layers[layer].copy()
+    return to_dense_matrix(m)
+
+
+def check_obs(rep_layer: List[str], rep_field: List[str]) -> Optional[str]:
+    """utils.py:139-170 — at most one 'obs' (label) representation."""
+    pos = [i for i, f in enumerate(rep_field) if f == "obs"]
+    if len(pos) > 1:
+        raise ValueError("'obs' occurs more than once in the list. Currently Spateo only support one label consistency.")
+    return rep_layer[pos[0]] if pos else None
+
+
+def check_rep_layer(samples, rep_layer="X", rep_field="layer") -> bool:
+    """utils.py:174-224 — True, or ValueError naming the missing representation."""
+    if isinstance(rep_layer, str):
+        rep_layer = [rep_layer]
+    if isinstance(rep_field, str):
+        rep_field = [rep_field] * len(rep_layer)
+    for sample in samples:
+        for rep, rep_f in zip(rep_layer, rep_field):
+            missing = False
+            if rep_f == "layer":
+                missing = (rep != "X") and (rep not in sample.layers)
+            elif rep_f == "obsm":
+                missing = rep not in sample.obsm
+            elif rep_f == "obs":
+                missing = rep not in sample.obs
+                if not missing and not isinstance(sample.obs[rep].dtype, pd.CategoricalDtype):
+                    raise ValueError(
+                        f"The specified representation '{rep}' found in the '{rep_f}' attribute should be categorical."
+                    )
+            else:
+                raise ValueError("rep_field must be either 'layer', 'obsm' or 'obs'")
+            if missing:
+                raise ValueError(
+                    f"The specified representation '{rep}' not found in the '{rep_f}' attribute of some of the AnnData objects."
+                )
+    return True
+
+
+def check_label_transfer_dict(catA, catB, label_transfer_dict):
+    """utils.py:228-260 — KeyError when a category pair is missing."""
+    for ca in catA:
+        if ca not in label_transfer_dict:
+            raise KeyError(f"Category '{ca}' from catA not found in label_transfer_dict.")
+        for cb in catB:
+            if cb not in label_transfer_dict[ca]:
+                raise KeyError(
+                    f"Category '{cb}' from catB not found in label_transfer_dict for category '{ca}' from catA."
+                )
+
+
+def generate_label_transfer_dict(
+    cat1, cat2, positive_pairs=None, negative_pairs=None, default_positive_value: float = 10.0,
+    default_negative_value: float = 1.0,
+) -> Dict[str, Dict[str, float]]:
+    """utils.py:376-437 — row-normalised label transfer prior (same defaults)."""
+    table = {c1: {c2: 1.0 for c2 in cat2} for c1 in cat1}
+    if positive_pairs is None and negative_pairs is None:
+        table = {c1: {c2: default_negative_value for c2 in cat2} for c1 in cat1}
+        positive_pairs = [{"left": [c], "right": [c], "value": default_positive_value} for c in np.union1d(cat1, cat2)]
+    for pairs in (positive_pairs, negative_pairs):
+        if pairs is None:
+            continue
+        for p in pairs:
+            for l in p["left"]:
+                for r in p["right"]:
+                    if r in table and l in table[r]:
+                        table[r][l] = p["value"]
+    out = {}
+    for c1 in cat1:
+        norm = np.array([table[c1][c2] for c2 in cat2]).sum()
+        out[c1] = {c2: table[c1][c2] / (norm + 1e-8) for c2 in cat2}
+    return out
+
+
+def check_label_transfer(sampleA, sampleB, obs_key: str, label_transfer_dict=None) -> np.ndarray:
+    """utils.py:296-312 — float32 matrix [len(catA), len(catB)]."""
+    if label_transfer_dict is not None and not isinstance(label_transfer_dict, dict):
+        raise ValueError("label_transfer_dict should be a list or a dictionary.")
+    catA = sampleA.obs[obs_key].cat.categories.tolist()
+    catB = sampleB.obs[obs_key].cat.categories.tolist()
+    if label_transfer_dict is None:
+        label_transfer_dict = generate_label_transfer_dict(catA, catB)
+    lt = np.zeros((len(catA), len(catB)), dtype=np.float32)
+    for j, ca in enumerate(catA):
+        for k, cb in enumerate(catB):
+            lt[j, k] = label_transfer_dict[ca][cb]
+    return lt
+
+
+def get_rep(sample, rep: str = "X", rep_field: str = "layer", genes=None, dtype=np.float32) -> np.ndarray:
+    """utils.py:441-486 — dense host matrix (layer/obsm) or int32 category codes (obs)."""
+    if rep_field == "layer":
+        return np.ascontiguousarray(check_exp(sample=sample[:, genes], layer=rep), dtype=dtype)
+    if rep_field == "obs":
+        return np.array(sample.obs[rep].cat.codes.values, dtype=np.int32)
+    if rep_field == "obsm":
+        return np.ascontiguousarray(np.asarray(sample.obsm[rep]), dtype=dtype)
+    raise ValueError("rep_field must be either 'layer', 'obsm' or 'obs'")
+
+
+def normalize_coords(coordsA: np.ndarray, coordsB: np.ndarray, separate_mean=True, separate_scale=False):
+    """morpho_class.py:589-635 — zero-mean per slice, RMS scale (shared by default). Returns new arrays + params."""
+    dt = coordsA.dtype
+    coords = [coordsA.copy(), coordsB.copy()]
+    D = coordsA.shape[1]
+    means = np.zeros((2, D), dtype=dt)
+    scales = np.zeros((2,), dtype=dt)
+    for i in range(2):
+        means[i] = coords[i].sum(axis=0, dtype=np.float64) / coords[i].shape[0]
+    if not separate_mean:
+        means = np.repeat(means.mean(axis=0), 2, axis=0)  # same (odd) behaviour as morpho_class.py:615
+    for i in range(2):
+        coords[i] -= means[i]
+        scales[i] = np.sqrt(np.sum(coords[i].astype(np.float64) ** 2) / coords[i].shape[0])
+    if not separate_scale:
+        scales = np.full((2,), scales.mean(), dtype=dt)
+    for i in range(2):
+        coords[i] /= scales[i]
+    return coords[0], coords[1], scales, means
+
+
+def voxel_data(coords: np.ndarray, gene_exp: np.ndarray, voxel_size: Optional[float] = None, voxel_num: int = 10000):
+    """utils.py:1283-1336, result-identical but without the Python loop over voxels.
+
+    Grid of ``int(sqrt(voxel_num))`` steps per axis; a cell belongs to EVERY grid point closer than ``voxel_size / 2``
+    (overlapping membership, not a partition). Candidate pairs come from a KD-tree with a slightly larger radius and are
+    then filtered with the reference's own expression evaluated in the input precision, so memberships are identical.
+    """
+    N, D = coords.shape
+    lo, hi = np.min(coords, axis=0), np.max(coords, axis=0)
+    if voxel_size is None:
+        voxel_size = np.sqrt(np.prod(hi - lo)) / (np.sqrt(N) / 5)
+    steps = (hi - lo) / int(np.sqrt(voxel_num))
+    axes = [np.arange(a, b, s) for a, b, s in zip(lo, hi, steps)]
+    grid = np.stack(np.meshgrid(*axes), axis=-1).reshape(-1, D)
+    radius = voxel_size / 2
+    tree = cKDTree(np.asarray(coords, dtype=np.float64))
+    cand = tree.query_ball_point(np.asarray(grid, dtype=np.float64), r=float(radius) * (1 + 1e-5) + 1e-12)
+    counts = np.fromiter((len(c) for c in cand), dtype=np.int64, count=len(cand))
+    vox_idx = np.repeat(np.arange(grid.shape[0]), counts)
+    cell_idx = np.fromiter((i for c in cand for i in c), dtype=np.int64, count=int(counts.sum()))
+    # exact membership test, same arithmetic as the reference (input dtype)
+    dist = np.sqrt(np.sum((coords[cell_idx] - grid[vox_idx]) ** 2, axis=1))
+    keep = dist < radius
+    vox_idx, cell_idx = vox_idx[keep], cell_idx[keep]
+    n_in = np.bincount(vox_idx, minlength=grid.shape[0])
+    used = n_in > 0
+    # voxel means as one sparse membership product (float64 accumulation), only for the non-empty voxels
+    from scipy.sparse import csr_matrix
+
+    new_id = np.cumsum(used) - 1
+    M = csr_matrix(
+        (1.0 / n_in[vox_idx].astype(np.float64), (new_id[vox_idx], cell_idx)), shape=(int(used.sum()), N)
+    )
+    means = M @ np.asarray(gene_exp, dtype=np.float64)
+    return grid[used, :], np.asarray(means)
+
+
+def inlier_from_NN(train_x, train_y, distance):
+    """utils.py:1220-1280 — annealed robust Procrustes on the mutual-NN voxel pairs (host, float64, tiny)."""
+    N, D = train_x.shape
+    distance = np.maximum(0, distance)
+    distance = distance / (np.max(distance) / (np.log(10) * 2))
+    alpha, alpha_end, max_iter = 1.0, 0.1, 100
+    alpha_dec = np.power(alpha_end / alpha, 1 / (max_iter - 20))
+    weight = np.exp(-distance * alpha)
+    init_weight = weight
+    P = np.ones((N, 1)) * weight
+    y_hat = train_x
+    sigma2 = np.sum((y_hat - train_y) ** 2) / (D * N)
+    gamma = 0.5
+    area = np.maximum(np.prod(train_x.max(0) - train_x.min(0)), np.prod(train_y.max(0) - train_y.min(0)))
+    Sp = P.sum()
+    R, t = np.eye(D), np.zeros(D)
+    for it in range(max_iter):
+        mu_x = (train_x * P).sum(0) / Sp
+        mu_y = (train_y * P).sum(0) / Sp
+        A = (train_y - mu_y).T @ ((train_x - mu_x) * P)
+        U, _, Vh = np.linalg.svd(A)
+        C = np.eye(D)
+        C[-1, -1] = np.linalg.det(U @ Vh)
+        R = U @ C @ Vh
+        t = mu_y - mu_x @ R.T
+        y_hat = train_x @ R.T + t
+        resid = np.sum((train_y - y_hat) ** 2, 1, keepdims=True)
+        term1 = np.exp(-resid / (2 * sigma2)) * weight
+        outlier = np.max(weight) * (1 - gamma) * np.power(2 * np.pi * sigma2, D / 2) / (gamma * area)
+        P = term1 / (term1 + outlier)
+        Sp = P.sum()
+        gamma = np.minimum(np.maximum(Sp / N, 0.01), 0.99)
+        P = np.maximum(P, 1e-6)
+        sigma2 = np.sum((y_hat - train_y) ** 2 * P) / (D * Sp)
+        if it > 20:
+            alpha = alpha * alpha_dec
+            weight = np.exp(-distance * alpha)
+            weight = weight / np.max(weight)
+    resid = np.sum((train_y - y_hat) ** 2, 1, keepdims=True)
+    term1 = np.exp(-resid / (2 * 1e-2)) * weight
+    outlier = np.max(weight) * (1 - 0.1) * np.power(2 * np.pi * 1e-2, D / 2) / (0.1 * area)
+    P = term1 / (term1 + outlier)
+    gamma = np.minimum(np.maximum(P.sum() / N, 0.01), 0.99)
+    return P, R, t, init_weight, sigma2, gamma
+
+
+def solve_RT_by_correspondence(X: np.ndarray, Y: np.ndarray, return_s: bool = False):
+    """spateo/alignment/utils.py:350-402 — least-squares R, t with X ~ Y R^T + t (no reflection guard, as there)."""
+    tX, tY = np.mean(X, axis=0), np.mean(Y, axis=0)
+    Xc, Yc = X - tX, Y - tY
+    H = Yc.T @ Xc
+    U, S, Vt = np.linalg.svd(H)
+    R = Vt.T @ U.T
+    t = np.mean(Xc, axis=0) - np.mean(Yc, axis=0) + tX - tY @ R.T
+    if return_s:
+        s = np.trace(Xc.T @ Xc - R.T @ (Yc.T @ Xc)) / np.trace(Yc.T @ Yc)
+        return R, t, s
+    return R, t
+
+
+def empty_cache(device: str = "cpu"):
+    """utils.py:1413-1415."""
+    import torch
+
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()

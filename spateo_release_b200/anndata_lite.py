@@ -111,7 +111,17 @@ class AnnDataLite:
             rkey, ckey = key, slice(None)
         ridx = self._row_index(rkey)
         cidx = self._col_index(ckey)
-        X = self.X[ridx][:, cidx]
+        n, g = self.shape
+        all_rows = len(ridx) == n and np.array_equal(ridx, np.arange(n))
+        all_cols = len(cidx) == g and np.array_equal(cidx, np.arange(g))
+        if all_rows and all_cols:
+            X = self.X  # a view, like anndata's lazy views; consumers copy when they need to
+        elif all_rows:
+            X = self.X[:, cidx]
+        elif all_cols:
+            X = self.X[ridx]
+        else:
+            X = self.X[ridx][:, cidx]
         return AnnDataLite(
             X=X,
             obs=self.obs.iloc[ridx],

@@ -1,0 +1,606 @@
+// M-step of the morpho-align EM on the device (spateo/alignment/methods/morpho_class.py:1202-1469): gamma / alpha
+// (digamma), the non-rigid inducing-point solve (U^T diag(K_NA) U contraction, symmetric eigen pseudo-inverse, field
+// application), the rigid Procrustes update from weighted moments, sigma2, and the per-row state refresh.
+// All scalar state lives in `spb_scalars` on the device: no host synchronisation inside an iteration.
+#include "common.cuh"
+
+namespace {
+
+constexpr double kLog2e = 1.4426950408889634;
+constexpr double kTwoPi = 6.283185307179586;
+
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void iter_begin_kernel(spb_em_params p, int iter) {
+  spb_scalars* sc = p.sc;
+  const int K = p.K;
+  for (int q = threadIdx.x; q < K * K; q += blockDim.x) p.UtWU[q] = 0.0;
+  for (int q = threadIdx.x; q < K * 3; q += blockDim.x) p.UtPXB[q] = 0.0;
+  for (int q = threadIdx.x; q < 32; q += blockDim.x) p.moments[q] = 0.0;
+  if (threadIdx.x == 0) {
+    sc->iter = iter;
+    sc->step = p.svi ? fmin(1.0, 10.0 / (iter + 1.0)) : 1.0;  // morpho_class.py:894
+    for (int q = 0; q < 8; ++q) sc->sums[q] = 0.0;
+    sc->dotKS = 0.0;
+    const double s2 = sc->sigma2, g = sc->gamma;
+    const double outlier_s = p.samples_s * (double)p.NA;                                   // utils.py:1051
+    sc->omega = pow(kTwoPi * s2, 0.5 * p.D) * (1.0 - g) / (g * outlier_s);                 // utils.py:1053
+    const double cq = -kLog2e / (2.0 * s2);
+    sc->c_q = (float)cq;
+    sc->c_s = (float)(cq * sc->sigma2_variance);                                           // utils.py:1049
+  }
+}
+
+// Sp running averages, sigma2_related, gamma (morpho_class.py:1178-1200, 1214-1224)
+__global__ void scalar_update_kernel(spb_em_params p) {
+  spb_scalars* sc = p.sc;
+  const double step = sc->step;
+  const double nsp = sc->sums[0], ns2 = sc->sums[1], nS = sc->sums[2], S2 = sc->sums[3];
+  if (p.svi) {
+    sc->Sp_spatial = step * nsp + (1.0 - step) * sc->Sp_spatial;
+    sc->Sp = step * nS + (1.0 - step) * sc->Sp;
+    sc->Sp_sigma2 = step * ns2 + (1.0 - step) * sc->Sp_sigma2;
+  } else {
+    sc->Sp_spatial = nsp;
+    sc->Sp = nS;
+    sc->Sp_sigma2 = ns2;
+  }
+  sc->SpK = nS;
+  sc->sigma2_related = S2 / ((double)p.D * sc->Sp_sigma2);
+  double g = exp(digamma_pos(p.gamma_a + sc->Sp_spatial) - digamma_pos(p.gamma_a + p.gamma_b + (double)p.NBb));
+  sc->gamma = fmax(fmin(g, 0.99), 0.01);
+}
+
+// alpha_i (morpho_class.py:1238-1252)
+__global__ void alpha_update_kernel(spb_em_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.NA) return;
+  const spb_scalars* sc = p.sc;
+  const double kap = (double)p.kappa[i];
+  const double a = exp(digamma_pos(kap + (double)p.K_NA_spatial[i]) - digamma_pos(kap * (double)p.NA + sc->Sp_spatial));
+  if (p.svi) {
+    const double step = sc->step;
+    p.alpha[i] = (float)(step * a + (1.0 - step) * (double)p.alpha[i]);
+  } else {
+    p.alpha[i] = (float)a;
+  }
+}
+
+// PXB_term = P@XB - RnA * K_NA (SVI: running average) (morpho_class.py:1270-1276)
+__global__ void pxb_term_kernel(spb_em_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.NA) return;
+  const double step = p.sc->step;
+  const float k = p.K_NA[i];
+  for (int d = 0; d < 3; ++d) {
+    const int64_t o = (int64_t)d * p.ldx + i;
+    const float nw = p.PXB[o] - p.RnA[o] * k;
+    p.PXB_term[o] = p.svi ? (float)(step * (double)nw + (1.0 - step) * (double)p.PXB_term[o]) : nw;
+  }
+}
+
+// U^T diag(K_NA) U  and  U^T PXB_term : 32x32 output tiles, fp64 accumulation, atomics into the K x K accumulator.
+// grid.x = row chunks, grid.y = (kt, lt) tile pairs with kt <= lt.
+constexpr int kAccRows = 128;
+__global__ void __launch_bounds__(256) nonrigid_accumulate_kernel(spb_em_params p, int rows_per_block, int ntile) {
+  __shared__ float Uk[32][kAccRows + 1];
+  __shared__ float Ul[32][kAccRows + 1];
+  __shared__ float Xs[3][kAccRows];
+  // decode the tile pair
+  int kt = 0, lt = 0;
+  {
+    int q = blockIdx.y;
+    for (kt = 0; kt < ntile; ++kt) {
+      const int cnt = ntile - kt;
+      if (q < cnt) {
+        lt = kt + q;
+        break;
+      }
+      q -= cnt;
+    }
+  }
+  const int K = p.K;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+  double accx = 0.0;  // U^T PXB_term entry (threads < 96 of diagonal tiles)
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(p.NA, r_begin + rows_per_block);
+  for (int r0 = r_begin; r0 < r_end; r0 += kAccRows) {
+    const int nr = min(kAccRows, r_end - r0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < 32 * kAccRows; q += 256) {
+      const int kk = q / kAccRows, rr = q % kAccRows;
+      const int k = kt * 32 + kk, l = lt * 32 + kk;
+      const bool ok = rr < nr;
+      const float w = ok ? p.K_NA[r0 + rr] : 0.f;
+      Uk[kk][rr] = (ok && k < K) ? p.UT[(int64_t)k * p.ldx + r0 + rr] : 0.f;
+      Ul[kk][rr] = (ok && l < K) ? p.UT[(int64_t)l * p.ldx + r0 + rr] * w : 0.f;
+    }
+    if (kt == lt) {
+      for (int q = threadIdx.x; q < 3 * kAccRows; q += 256) {
+        const int d = q / kAccRows, rr = q % kAccRows;
+        Xs[d][rr] = rr < nr ? p.PXB_term[(int64_t)d * p.ldx + r0 + rr] : 0.f;
+      }
+    }
+    __syncthreads();
+    for (int rr = 0; rr < kAccRows; ++rr) {
+      const double a0 = Uk[2 * ty][rr], a1 = Uk[2 * ty + 1][rr];
+      const double b0 = Ul[2 * tx][rr], b1 = Ul[2 * tx + 1][rr];
+      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+    }
+    if (kt == lt && threadIdx.x < 96) {
+      const int kk = threadIdx.x / 3, d = threadIdx.x % 3;
+      for (int rr = 0; rr < kAccRows; ++rr) accx += (double)Uk[kk][rr] * (double)Xs[d][rr];
+    }
+  }
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      const int k = kt * 32 + 2 * ty + a, l = lt * 32 + 2 * tx + b;
+      if (k < K && l < K) {
+        atomicAdd(&p.UtWU[(int64_t)k * K + l], acc[a][b]);
+        if (kt != lt) atomicAdd(&p.UtWU[(int64_t)l * K + k], acc[a][b]);
+      }
+    }
+  if (kt == lt && threadIdx.x < 96) {
+    const int k = kt * 32 + threadIdx.x / 3, d = threadIdx.x % 3;
+    if (k < K) atomicAdd(&p.UtPXB[k * 3 + d], accx);
+  }
+}
+
+// SigmaInv = sigma2 lambda Gamma + U^T W U (SVI running average) (morpho_class.py:1266-1277)
+__global__ void nonrigid_blend_kernel(spb_em_params p) {
+  const int K = p.K;
+  const spb_scalars* sc = p.sc;
+  const double step = sc->step, s2l = sc->sigma2 * p.lambdaVF;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < K * K; q += gridDim.x * blockDim.x) {
+    const double nw = s2l * (double)p.Gamma[q] + p.UtWU[q];
+    p.SigmaInv[q] = p.svi ? step * nw + (1.0 - step) * p.SigmaInv[q] : nw;
+  }
+}
+
+// Symmetric eigen-decomposition by parallel cyclic Jacobi in shared memory (K <= 64), pseudo-inverse with scipy's
+// cutoff rtol = K * eps(float32) (scipy.linalg.pinv on the reference's fp32 matrix, utils.py:1435), Coff = Sigma UPXB.
+__global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
+  extern __shared__ double sh[];
+  const int K = p.K;
+  const int Kp = (K + 1) & ~1;
+  double* A = sh;                  // [Kp][Kp]
+  double* V = A + Kp * Kp;         // [Kp][Kp]
+  double* cs = V + Kp * Kp;        // [Kp] (c, s) per pair
+  int* top = reinterpret_cast<int*>(cs + Kp);
+  int* bot = top + Kp / 2;
+  __shared__ double s_off, s_diag;
+  const spb_scalars* sc = p.sc;
+  const double step = sc->step, s2l = sc->sigma2 * p.lambdaVF;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int q = tid; q < Kp * Kp; q += nt) {
+    const int r = q / Kp, c = q % Kp;
+    double a = 0.0;
+    if (r < K && c < K) {
+      const double nw = s2l * (double)p.Gamma[r * K + c] + p.UtWU[r * K + c];
+      a = p.svi ? step * nw + (1.0 - step) * p.SigmaInv[r * K + c] : nw;
+      p.SigmaInv[r * K + c] = a;
+    }
+    A[q] = a;
+    V[q] = (r == c) ? 1.0 : 0.0;
+  }
+  if (tid < Kp / 2) {
+    top[tid] = 2 * tid;
+    bot[tid] = 2 * tid + 1;
+  }
+  __syncthreads();
+  // symmetrise (atomics order may differ between the two triangles by rounding)
+  for (int q = tid; q < Kp * Kp; q += nt) {
+    const int r = q / Kp, c = q % Kp;
+    if (r < c) {
+      const double m = 0.5 * (A[r * Kp + c] + A[c * Kp + r]);
+      A[r * Kp + c] = m;
+      A[c * Kp + r] = m;
+    }
+  }
+  __syncthreads();
+  const int npair = Kp / 2;
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    if (tid == 0) {
+      double off = 0, dg = 0;
+      for (int r = 0; r < Kp; ++r)
+        for (int c = 0; c < Kp; ++c) {
+          const double a = A[r * Kp + c];
+          if (r == c) dg += a * a; else off += a * a;
+        }
+      s_off = off;
+      s_diag = dg;
+    }
+    __syncthreads();
+    if (s_off <= 1e-40 * s_diag || s_off == 0.0) break;
+    for (int stp = 0; stp < Kp - 1; ++stp) {
+      if (tid < npair) {
+        const int pp = min(top[tid], bot[tid]), qq = max(top[tid], bot[tid]);
+        const double apq = A[pp * Kp + qq];
+        double c = 1.0, s = 0.0;
+        if (fabs(apq) > 1e-300) {
+          const double theta = (A[qq * Kp + qq] - A[pp * Kp + pp]) / (2.0 * apq);
+          const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+          c = 1.0 / sqrt(t * t + 1.0);
+          s = t * c;
+        }
+        cs[2 * tid] = c;
+        cs[2 * tid + 1] = s;
+      }
+      __syncthreads();
+      // rows: A <- J^T A
+      for (int q = tid; q < npair * Kp; q += nt) {
+        const int pr = q / Kp, k = q % Kp;
+        const int pp = min(top[pr], bot[pr]), qq = max(top[pr], bot[pr]);
+        const double c = cs[2 * pr], s = cs[2 * pr + 1];
+        const double ap = A[pp * Kp + k], aq = A[qq * Kp + k];
+        A[pp * Kp + k] = c * ap - s * aq;
+        A[qq * Kp + k] = s * ap + c * aq;
+      }
+      __syncthreads();
+      // columns: A <- A J, V <- V J
+      for (int q = tid; q < npair * Kp; q += nt) {
+        const int pr = q / Kp, k = q % Kp;
+        const int pp = min(top[pr], bot[pr]), qq = max(top[pr], bot[pr]);
+        const double c = cs[2 * pr], s = cs[2 * pr + 1];
+        const double ap = A[k * Kp + pp], aq = A[k * Kp + qq];
+        A[k * Kp + pp] = c * ap - s * aq;
+        A[k * Kp + qq] = s * ap + c * aq;
+        const double vp = V[k * Kp + pp], vq = V[k * Kp + qq];
+        V[k * Kp + pp] = c * vp - s * vq;
+        V[k * Kp + qq] = s * vp + c * vq;
+      }
+      __syncthreads();
+      // round-robin tournament rotation of the index sets
+      if (tid == 0) {
+        const int last_top = top[npair - 1];
+        const int first_bot = bot[0];
+        for (int q = npair - 1; q >= 2; --q) top[q] = top[q - 1];
+        if (npair > 1) top[1] = first_bot;
+        for (int q = 0; q < npair - 1; ++q) bot[q] = bot[q + 1];
+        bot[npair - 1] = last_top;
+        if (npair == 1) { /* single pair: nothing to rotate */ bot[0] = first_bot; }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  // eigenvalues on the diagonal of A; invert above the cutoff
+  if (tid == 0) {
+    double mx = 0;
+    for (int r = 0; r < K; ++r) mx = fmax(mx, fabs(A[r * Kp + r]));
+    s_diag = mx * (double)K * 1.1920928955078125e-07;
+  }
+  __syncthreads();
+  const double cutoff = s_diag;
+  for (int r = tid; r < Kp; r += nt) {
+    const double ev = (r < K) ? A[r * Kp + r] : 0.0;
+    cs[r] = (r < K && fabs(ev) > cutoff) ? 1.0 / ev : 0.0;
+  }
+  __syncthreads();
+  for (int q = tid; q < K * K; q += nt) {
+    const int r = q / K, c = q % K;
+    double s = 0;
+    for (int e = 0; e < Kp; ++e) s += V[r * Kp + e] * cs[e] * V[c * Kp + e];
+    p.Sigma[q] = s;
+  }
+  __syncthreads();
+  __threadfence_block();
+  for (int q = tid; q < K * 3; q += nt) {
+    const int r = q / 3, d = q % 3;
+    double s = 0;
+    for (int c = 0; c < K; ++c) {
+      double sg = 0;
+      for (int e = 0; e < Kp; ++e) sg += V[r * Kp + e] * cs[e] * V[c * Kp + e];
+      s += sg * p.UtPXB[c * 3 + d];
+    }
+    p.Coff[q] = s;
+  }
+}
+
+// VnA = U Coff, SigmaDiag = sigma2 * diag(U Sigma U^T) (morpho_class.py:1293-1298)
+__global__ void __launch_bounds__(128) field_apply_kernel(spb_em_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.NA) return;
+  const int K = p.K;
+  const double s2 = p.sc->sigma2;
+  double v0 = 0, v1 = 0, v2 = 0, quad = 0;
+  for (int k = 0; k < K; ++k) {
+    const double uk = (double)p.UT[(int64_t)k * p.ldx + i];
+    v0 += uk * p.Coff[k * 3 + 0];
+    v1 += uk * p.Coff[k * 3 + 1];
+    v2 += uk * p.Coff[k * 3 + 2];
+    double tk = 0;
+    for (int l = 0; l < K; ++l) tk += p.Sigma[(int64_t)k * K + l] * (double)p.UT[(int64_t)l * p.ldx + i];
+    quad += uk * tk;
+  }
+  p.VnA[i] = (float)v0;
+  p.VnA[p.ldx + i] = (float)v1;
+  p.VnA[2 * p.ldx + i] = (float)v2;
+  p.SigmaDiag[i] = (float)(s2 * quad);
+}
+
+// weighted moments for the rigid update and sigma2 (morpho_class.py:1312-1318, 1356-1357, 1427)
+//  [0..2] sum K x   [3..5] sum K v   [6..8] sum (P@XB)_i   [9..17] sum K x v^T   [18..26] sum x (P@XB)_i^T
+//  [27] sum K_NA_sigma2 * SigmaDiag   [28] sum K
+__global__ void __launch_bounds__(256) rigid_moments_kernel(spb_em_params p) {
+  double m[29];
+#pragma unroll
+  for (int q = 0; q < 29; ++q) m[q] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.NA; i += gridDim.x * blockDim.x) {
+    const double k = p.K_NA[i];
+    double x[3], v[3], px[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      x[d] = p.xa[(int64_t)d * p.ldx + i];
+      v[d] = p.VnA[(int64_t)d * p.ldx + i];
+      px[d] = p.PXB[(int64_t)d * p.ldx + i];
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      m[d] += k * x[d];
+      m[3 + d] += k * v[d];
+      m[6 + d] += px[d];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        m[9 + d * 3 + e] += k * x[d] * v[e];
+        m[18 + d * 3 + e] += x[d] * px[e];
+      }
+    }
+    m[27] += (double)p.K_NA_sigma2[i] * (double)p.SigmaDiag[i];
+    m[28] += k;
+  }
+  block_reduce_atomic<29>(m, p.moments);
+}
+
+// rotation / translation / sigma2 (morpho_class.py:1320-1402, 1426-1435) — one thread, fp64
+__global__ void rigid_solve_kernel(spb_em_params p, int iter) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  spb_scalars* sc = p.sc;
+  const int D = p.D;
+  const double* m = p.moments;
+  const double Sp = sc->Sp, SpK = m[28];
+  double PXA[3], PVA[3], PXB[3];
+  for (int d = 0; d < 3; ++d) {
+    PXA[d] = m[d];
+    PVA[d] = m[3 + d];
+    PXB[d] = m[6 + d];
+  }
+  double c = 0.0;
+  double PXAa[3], PXBa[3];  // the "augmented" arrays of the reference's aliasing quirk
+  double deno = Sp;
+  for (int d = 0; d < 3; ++d) {
+    PXAa[d] = PXA[d];
+    PXBa[d] = PXB[d];
+  }
+  if (p.nn_init) {
+    c = sc->sigma2 * p.nn_init_weight * Sp / p.inl_SP;
+    for (int d = 0; d < 3; ++d) {
+      PXBa[d] += c * p.inl_Sb[d];
+      PXAa[d] += c * p.inl_Sa[d];
+    }
+    deno += c * p.inl_SP;
+  }
+  double muB[3], muA[3], muV[3];
+  for (int d = 0; d < 3; ++d) {
+    muB[d] = PXBa[d] / deno;
+    muA[d] = PXAa[d] / deno;
+    muV[d] = PVA[d] / Sp;
+  }
+  double A[9];
+  for (int q = 0; q < 9; ++q) A[q] = 0.0;
+  for (int d1 = 0; d1 < D; ++d1)
+    for (int d2 = 0; d2 < D; ++d2) {
+      const double T1 = m[9 + d1 * 3 + d2] - muA[d1] * PVA[d2] - PXA[d1] * muV[d2] + SpK * muA[d1] * muV[d2];
+      const double T2 = m[18 + d1 * 3 + d2] - muA[d1] * PXB[d2] - PXA[d1] * muB[d2] + SpK * muA[d1] * muB[d2];
+      double a = T2 - T1;  // -(T1 - T2), transposed below
+      if (p.nn_init) {
+        const double E = -(p.inl_Mab[d1 * 3 + d2] - muA[d1] * p.inl_Sb[d2] - p.inl_Sa[d1] * muB[d2] +
+                           p.inl_SP * muA[d1] * muB[d2]);
+        a -= c * E;
+      }
+      A[d2 * 3 + d1] = a;
+    }
+  double Rn[9];
+  rotation_from(A, D, Rn);
+  const double step = sc->step;
+  const bool blend = p.svi && step < 1.0;
+  if (p.update_R) {
+    for (int d1 = 0; d1 < D; ++d1)
+      for (int d2 = 0; d2 < D; ++d2) {
+        const int q = d1 * 3 + d2;
+        sc->R[q] = blend ? step * Rn[q] + (1.0 - step) * sc->R[q] : Rn[q];
+      }
+  }
+  double tn[3];
+  double tden = Sp;
+  for (int d = 0; d < D; ++d) {
+    double s = PXBa[d] - PVA[d];
+    for (int e = 0; e < D; ++e) s -= PXAa[e] * sc->R[d * 3 + e];
+    if (p.nn_init) {
+      double r = p.inl_Sb[d];
+      for (int e = 0; e < D; ++e) r -= p.inl_Sa[e] * sc->R[d * 3 + e];
+      s += c * r;
+    }
+    tn[d] = s;
+  }
+  if (p.nn_init) tden += c * p.inl_SP;
+  for (int d = 0; d < D; ++d) {
+    const double t = tn[d] / tden;
+    sc->t[d] = blend ? step * t + (1.0 - step) * sc->t[d] : t;
+  }
+  // sigma2 (morpho_class.py:1426-1435)
+  sc->dotKS = m[27];
+  double s2 = fmax(sc->sigma2_related + m[27] / sc->Sp_sigma2, 1e-3);
+  sc->sigma2_variance = fmin(sc->sigma2_variance * p.sigma2_variance_decress, p.sigma2_variance_end);
+  if (iter < 100) s2 = fmax(s2, 1e-2);
+  sc->sigma2 = s2;
+  if (p.trace && p.trace_buf) {
+    double* tr = p.trace_buf + (int64_t)iter * SPB_TRACE_STRIDE;
+    tr[0] = sc->sigma2; tr[1] = sc->gamma; tr[2] = sc->Sp; tr[3] = sc->Sp_spatial;
+    tr[4] = sc->Sp_sigma2; tr[5] = sc->sigma2_variance; tr[6] = sc->sigma2_related; tr[7] = sc->step;
+  }
+}
+
+// RnA = XA R^T + t, XAHat = VnA + RnA, and next E-step's model multiplier (morpho_class.py:1404, 293, 1087)
+__global__ void row_update_kernel(spb_em_params p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.NA) return;
+  const spb_scalars* sc = p.sc;
+  float x[3];
+  for (int d = 0; d < 3; ++d) x[d] = p.xa[(int64_t)d * p.ldx + i];
+  for (int d = 0; d < 3; ++d) {
+    float r = 0.f;
+    if (d < p.D) {
+      double s = sc->t[d];
+      for (int e = 0; e < p.D; ++e) s += (double)x[e] * sc->R[d * 3 + e];
+      r = (float)s;
+    }
+    const int64_t o = (int64_t)d * p.ldx + i;
+    p.RnA[o] = r;
+    p.XAHat[o] = p.VnA[o] + r;
+  }
+  const double a = (double)p.alpha[i], sd = (double)p.SigmaDiag[i], s2 = sc->sigma2;
+  p.mm[i] = (float)(a * exp(-sd / s2));
+  p.lm[i] = (float)(log2(a) - sd * kLog2e / s2);
+}
+
+// closing similarity (morpho_class.py:1451-1468) from the last E-step's moments
+__global__ void optimal_rigid_kernel(spb_em_params p, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const spb_scalars* sc = p.sc;
+  const int D = p.D;
+  const double* m = p.moments;
+  const double Sp = sc->Sp, SpK = m[28];
+  double muA[3], muB[3];
+  for (int d = 0; d < 3; ++d) {
+    muA[d] = m[d] / Sp;
+    muB[d] = m[6 + d] / Sp;
+  }
+  double A[9];
+  for (int q = 0; q < 9; ++q) A[q] = 0.0;
+  for (int d1 = 0; d1 < D; ++d1)
+    for (int d2 = 0; d2 < D; ++d2)
+      A[d1 * 3 + d2] = m[18 + d2 * 3 + d1] - m[6 + d1] * muA[d2] - muB[d1] * m[d2] + SpK * muB[d1] * muA[d2];
+  double R[9];
+  for (int q = 0; q < 9; ++q) R[q] = 0.0;
+  rotation_from(A, D, R);
+  for (int q = 0; q < 9; ++q) out[q] = R[q];
+  for (int d = 0; d < 3; ++d) {
+    double s = 0.0;
+    if (d < D) {
+      s = muB[d];
+      for (int e = 0; e < D; ++e) s -= muA[e] * R[d * 3 + e];
+    }
+    out[9 + d] = s;
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+extern "C" int spb_iter_begin(const spb_em_params* p, int32_t iter, void* stream) {
+  iter_begin_kernel<<<1, 256, 0, ST>>>(*p, iter);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_update_gamma_alpha(const spb_em_params* p, void* stream) {
+  scalar_update_kernel<<<1, 1, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  alpha_update_kernel<<<(p->NA + 255) / 256, 256, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
+  pxb_term_kernel<<<(p->NA + 255) / 256, 256, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  const int ntile = (p->K + 31) / 32;
+  const int npairs = ntile * (ntile + 1) / 2;
+  int rows_per_block = 2048;
+  dim3 grid((p->NA + rows_per_block - 1) / rows_per_block, npairs);
+  nonrigid_accumulate_kernel<<<grid, 256, 0, ST>>>(*p, rows_per_block, ntile);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_nonrigid_blend(const spb_em_params* p, void* stream) {
+  nonrigid_blend_kernel<<<(p->K * p->K + 255) / 256, 256, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
+  if (p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
+  const int Kp = (p->K + 1) & ~1;
+  const size_t smem = sizeof(double) * (2 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(nonrigid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  nonrigid_solve_kernel<<<1, 256, smem, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_field_apply(const spb_em_params* p, void* stream) {
+  field_apply_kernel<<<(p->NA + 127) / 128, 128, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_rigid_moments(const spb_em_params* p, void* stream) {
+  int blocks = (p->NA + 255) / 256;
+  if (blocks > 592) blocks = 592;
+  rigid_moments_kernel<<<blocks, 256, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_rigid_solve(const spb_em_params* p, int32_t iter, void* stream) {
+  rigid_solve_kernel<<<1, 32, 0, ST>>>(*p, iter);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_row_update(const spb_em_params* p, void* stream) {
+  row_update_kernel<<<(p->NA + 255) / 256, 256, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_optimal_rigid(const spb_em_params* p, double* out12, void* stream) {
+  optimal_rigid_kernel<<<1, 32, 0, ST>>>(*p, out12);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+#define SPB_TRY(x)          \
+  do {                      \
+    int rc__ = (x);         \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream) {
+  const bool nonrigid = iter > p->nonrigid_start_iter;  // latched flag == monotone in iter (morpho_class.py:289-291)
+  if (nonrigid && p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
+  SPB_TRY(spb_iter_begin(p, iter, stream));
+  SPB_TRY(spb_gather_cols(p, iter, stream));
+  SPB_TRY(spb_estep_sweep1(p, iter, stream));
+  SPB_TRY(spb_col_finalize(p, stream));
+  SPB_TRY(spb_estep_sweep2(p, iter, stream));
+  SPB_TRY(spb_row_finalize(p, stream));
+  SPB_TRY(spb_update_gamma_alpha(p, stream));
+  if (nonrigid) {
+    SPB_TRY(spb_nonrigid_accumulate(p, stream));
+    SPB_TRY(spb_nonrigid_solve(p, stream));
+    SPB_TRY(spb_field_apply(p, stream));
+  }
+  SPB_TRY(spb_rigid_moments(p, stream));
+  SPB_TRY(spb_rigid_solve(p, iter, stream));
+  SPB_TRY(spb_row_update(p, stream));
+  return 0;
+}

@@ -1,0 +1,342 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden reference fixtures.
+
+Tolerances (north_star): posterior / transport matrix 1e-4 relative for ONE E-step on identical inputs against the
+float64 oracle; aligned coordinates 1e-3 relative for whole runs. Whole-run P is compared against the float64
+reference with the reference's own fp32-vs-fp64 deviation printed beside it (the fp32 reference itself sits ~1e-3 away
+from its fp64 twin after 100+ iterations — SURVEY.md Appendix F).
+"""
+
+import ast
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import morpho_oracle as mo  # noqa: E402
+
+
+def _adata_from_golden(g):
+    import pandas as pd
+
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    G = g["exp_moving"].shape[1]
+    var = pd.DataFrame(index=[f"g{i}" for i in range(G)])
+    mov = AnnDataLite(g["exp_moving"], var=var.copy(), obsm={"spatial": g["raw_coords_moving"]})
+    fix = AnnDataLite(g["exp_fixed"], var=var.copy(), obsm={"spatial": g["raw_coords_fixed"]})
+    return mov, fix
+
+
+def _cfg(g):
+    return ast.literal_eval(str(g["cfg"]))
+
+
+def _model(g, **over):
+    import spateo_release_b200 as st
+
+    cfg = _cfg(g)
+    mov, fix = _adata_from_golden(g)
+    kw = dict(SVI_mode=cfg["svi"], max_iter=cfg["max_iter"], K=cfg["K"], verbose=False, device="0", vecfld_key_added="vf")
+    kw.update(cfg["kw"])
+    kw.update(over)
+    np.random.seed(0)
+    return st.align.Morpho_pairwise(sampleA=mov, sampleB=fix, **kw)
+
+
+def _relF(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _relmax(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def test_gene_cost_kl_matches_oracle(golden):
+    import torch
+
+    from spateo_release_b200 import _capi
+    from spateo_release_b200.alignment.morpho_class import GeneCostBuilder
+
+    g = golden("2d_full")
+    lib = _capi.load_library()
+    dev = torch.device("cuda", 0)
+    A = torch.from_numpy(g["exp_moving"]).to(dev)
+    B = torch.from_numpy(g["exp_fixed"]).to(dev)
+    gc = GeneCostBuilder(lib, dev)
+    opA, rtA = gc.prepare(A, "kl", fixed=False)
+    opB, rtB = gc.prepare(B, "kl", fixed=True)
+    NA, NB, G = A.shape[0], B.shape[0], A.shape[1]
+    ldx = 1024
+    GT = torch.full((NB, ldx), -1.0, dtype=torch.float32, device=dev)
+    beta2 = float(g["pre_beta2"])
+    gc.cost(opA, rtA, opB, rtB, NA, NB, G, "kl", "gauss", beta2, False, GT, ldx)
+    torch.cuda.synchronize()
+    got = GT.cpu().numpy()
+    [e64] = mo.calc_distance(g["exp_moving"].astype(np.float64), g["exp_fixed"].astype(np.float64), "kl")
+    want = np.exp(-e64 / (2 * beta2)).T
+    assert np.all(got[:, NA:] == 0.0), "pad columns must be zero"
+    assert _relmax(got[:, :NA], want) < 2e-5
+    # raw distances ('prob' mode) against the reference's own fp32 matrix
+    gc.cost(opA, rtA, opB, rtB, NA, NB, G, "kl", "prob", None, False, GT, ldx)
+    torch.cuda.synchronize()
+    assert np.abs(GT.cpu().numpy()[:, :NA] - g["exp_dist"].T).max() < 5e-6
+
+
+@pytest.mark.parametrize("metric", ["euc", "cos", "square_euc"])
+def test_gene_cost_other_metrics(metric):
+    import torch
+
+    from spateo_release_b200 import _capi
+    from spateo_release_b200.alignment.morpho_class import GeneCostBuilder
+
+    rng = np.random.default_rng(0)
+    Xa = rng.normal(size=(333, 37)).astype(np.float32)
+    Xb = rng.normal(size=(290, 37)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    gc = GeneCostBuilder(_capi.load_library(), dev)
+    A, B = torch.from_numpy(Xa).to(dev), torch.from_numpy(Xb).to(dev)
+    opA, rtA = gc.prepare(A, metric, fixed=False)
+    opB, rtB = gc.prepare(B, metric, fixed=True)
+    GT = torch.empty((290, 1024), dtype=torch.float32, device=dev)
+    gc.cost(opA, rtA, opB, rtB, 333, 290, 37, metric, "prob", None, False, GT, 1024)
+    [want] = mo.calc_distance(Xa.astype(np.float64), Xb.astype(np.float64), metric)
+    assert np.abs(GT.cpu().numpy()[:, :333] - want.T).max() < 2e-4 * max(1.0, np.abs(want).max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _poke_estep_state(m, g, it, sfx=""):
+    """Overwrite the device state with the reference's E-step inputs at iteration ``it``."""
+    import torch
+
+    from spateo_release_b200._capi import SpbScalars
+
+    s, NA, D = m._state, m.NA, m.D
+    dev = m._dev
+    XAHat = g[f"it{it}_in_XAHat{sfx}"].astype(np.float32)
+    alpha = g[f"it{it}_in_alpha{sfx}"].astype(np.float64)
+    SigmaDiag = g[f"it{it}_in_SigmaDiag{sfx}"].astype(np.float64)
+    sigma2 = float(g[f"it{it}_in_sigma2{sfx}"])
+    s["XAHat"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(XAHat.T)).to(dev)
+    s["alpha"][:NA] = torch.from_numpy(alpha.astype(np.float32)).to(dev)
+    s["SigmaDiag"][:NA] = torch.from_numpy(SigmaDiag.astype(np.float32)).to(dev)
+    mmv = alpha * np.exp(-SigmaDiag / sigma2)
+    s["mm"][:NA] = torch.from_numpy(mmv.astype(np.float32)).to(dev)
+    s["lm"][:NA] = torch.from_numpy(np.log2(mmv).astype(np.float32)).to(dev)
+    s["xb4"][:, :D] = torch.from_numpy(g["pre_coordsB" + sfx].astype(np.float32)).to(dev)
+    sc = m._read_scalars()
+    sc.sigma2, sc.gamma = sigma2, float(g[f"it{it}_in_gamma{sfx}"])
+    sc.sigma2_variance = float(g[f"it{it}_in_sigma2_variance{sfx}"])
+    s["sc"].copy_(torch.from_numpy(np.frombuffer(bytes(sc), dtype=np.uint8).copy()))
+    m._params.samples_s = float(g["pre_samples_s" + sfx])
+
+
+@pytest.mark.parametrize("case", ["2d_full", "3d_full_warp"])
+@pytest.mark.parametrize("it", [0, 95])
+def test_single_estep_matches_float64_oracle(golden, case, it):
+    """One E-step on the reference's own inputs: P, K_NA, K_NB, K_NA_spatial, K_NA_sigma2 within 1e-4 of the fp64
+    oracle (and the fp32 reference's deviation from the same oracle printed for scale)."""
+    import torch
+
+    g = golden(case)
+    m = _model(g, probability_parameters=[float(g["pre_beta2"])])
+    m.prepare()
+    _poke_estep_state(m, g, it)
+    st = torch.cuda.current_stream().cuda_stream
+    m._estep_only(it, C.c_void_p(st))
+    torch.cuda.synchronize()
+    NA, NB = m.NA, m.NB
+    Pd = torch.empty((NA, NB), dtype=torch.float32, device=m._dev)
+    from spateo_release_b200._capi import check, ptr
+
+    check(m._lib.spb_materialize_P(C.byref(m._params), it, ptr(Pd), NB, C.c_void_p(st)), "materialize")
+    P = Pd.cpu().numpy()
+    # float64 oracle on the same (fp32-valued) inputs
+    f8 = lambda k: g[k].astype(np.float64)
+    XAHat, alpha, SD = f8(f"it{it}_in_XAHat"), f8(f"it{it}_in_alpha"), f8(f"it{it}_in_SigmaDiag")
+    sigma2, gamma = float(g[f"it{it}_in_sigma2"]), float(g[f"it{it}_in_gamma"])
+    yb = f8("pre_coordsB")
+    spatial = ((XAHat[:, None, :] - yb[None, :, :]) ** 2).sum(-1)
+    [ed] = mo.calc_distance(f8("exp_moving"), f8("exp_fixed"), "kl")
+    P64, kns, kn2, s2r = mo.get_P_core(
+        Dim=float(m.D), spatial_dist=spatial, exp_dist=[ed], sigma2=sigma2, model_mul=(alpha * np.exp(-SD / sigma2))[:, None],
+        gamma=gamma, samples_s=float(g["pre_samples_s"]), sigma2_variance=float(g[f"it{it}_in_sigma2_variance"]),
+        probability_type=["gauss"], probability_parameters=[float(g["pre_beta2"])],
+    )
+    ref32 = g[f"it{it}_out_P"]
+    print(f"\n[{case} it{it}] P relF ours-vs-f64 {_relF(P, P64):.2e} | ref32-vs-f64 {_relF(ref32, P64):.2e} | "
+          f"max-abs ours {np.abs(P - P64).max():.2e} (Pmax {P64.max():.2e})")
+    assert _relF(P, P64) < 1e-4
+    assert np.abs(P - P64).max() < 1e-4 * P64.max()
+    assert _relmax(m._state["K_NA"][:NA].cpu().numpy(), P64.sum(1)) < 1e-4
+    assert _relmax(m._state["K_NB"][:NB].cpu().numpy(), P64.sum(0)) < 1e-4
+    assert _relmax(m._state["K_NA_spatial"][:NA].cpu().numpy(), kns) < 1e-4
+    assert _relmax(m._state["K_NA_sigma2"][:NA].cpu().numpy(), kn2) < 1e-4
+    pxb = m._state["PXB"][: m.D, :NA].T.cpu().numpy()
+    assert _relmax(pxb, P64 @ yb) < 1e-4
+    sc = m._read_scalars()
+    assert abs(sc.sums[3] - s2r) < 1e-4 * abs(s2r)
+    assert abs(sc.sums[2] - P64.sum()) < 1e-5 * P64.sum()
+
+
+@pytest.mark.parametrize("case", ["2d_full", "3d_full_warp", "2d_full_nonn_euc", "3d_svi"])
+def test_full_run_matches_reference(golden, case):
+    """Whole alignment through the public class: aligned coordinates within 1e-3 (relative to the coordinate range)
+    of BOTH the float32 and the float64 reference runs; sigma2 / gamma close; P against the float64 reference."""
+    g = golden(case)
+    m = _model(g)
+    P = m.run()
+    for sfx in ("", "_f64"):
+        scale = np.abs(g["final_optimal_RnA" + sfx]).max()
+        for key in ("optimal_RnA", "XAHat", "RnA"):
+            err = np.abs(getattr(m, key) - g[f"final_{key}{sfx}"]).max() / scale
+            print(f"[{case}{sfx}] {key}: {err:.2e}")
+            assert err < 1e-3, (key, sfx, err)
+        assert abs(float(m.sigma2) - float(g["final_sigma2" + sfx])) < 2e-2 * float(g["final_sigma2" + sfx])
+        assert abs(float(m.gamma) - float(g["final_gamma" + sfx])) < 1e-2
+    assert _relmax(m.optimal_R, g["final_optimal_R_f64"]) < 1e-3
+    if "final_P_f64" in g:
+        ours = _relF(P, g["final_P_f64"])
+        theirs = _relF(g["final_P"], g["final_P_f64"])
+        print(f"[{case}] final P relF: ours-vs-ref64 {ours:.2e}, ref32-vs-ref64 {theirs:.2e}")
+        assert ours < max(3 * theirs, 5e-3)
+    else:
+        assert _relmax(P.sum(0), g["final_P_colsum_f64"]) < 2e-2
+    # vecfld schema (morpho_class.py:1507-1528)
+    for k in ("R", "t", "optimal_R", "optimal_t", "init_R", "init_t", "beta", "Coff", "inducing_variables",
+              "normalize_scales", "normalize_means", "normalize_c", "dissimilarity", "sigma2", "gamma", "NA",
+              "sigma2_variance", "method", "norm_dict", "kernel_type"):
+        assert k in m.vecfld
+    assert m.vecfld["t"].shape == (1, m.D) and m.vecfld["Coff"].shape == (m.K, m.D)
+
+
+def test_trajectory_tracks_reference(golden):
+    """Per-iteration sigma2 / gamma / Sp of the device loop against the float64 reference trajectory."""
+    g = golden("2d_full")
+    m = _model(g)
+    m.run()
+    tr = m.trace
+    n = tr.shape[0]
+    assert np.abs(tr[:, 0] - g["traj_sigma2_f64"][:n]).max() < 2e-2 * g["traj_sigma2_f64"].max()
+    assert np.abs(tr[:, 1] - g["traj_gamma_f64"][:n]).max() < 1e-2
+    assert np.abs(tr[:, 2] - g["traj_Sp_f64"][:n]).max() < 1e-2 * g["traj_Sp_f64"].max()
+
+
+def test_svi_batch_schedule_and_shapes(golden):
+    g = golden("3d_svi")
+    m = _model(g, max_iter=12)
+    P = m.run()
+    bs = int(g["pre_batch_size"])
+    assert P.shape == (m.NA, bs)  # SVI returns the last batch's columns (morpho_class.py:300-302 not taken)
+    sched = m._state["batch_idx"].cpu().numpy()
+    perm = g["pre_batch_perm"].copy()
+    for it in range(12):
+        assert np.array_equal(sched[it], perm[:bs])
+        perm = np.roll(perm, bs)
+
+
+def test_return_mapping_gives_full_posterior(golden):
+    g = golden("3d_svi")
+    m = _model(g, max_iter=15, return_mapping=True)
+    P = m.run()
+    assert P.shape == (m.NA, m.NB)
+    assert np.all(P.sum(0) <= 1.0 + 1e-4) and abs(P.sum() - m.K_NA.sum()) < 1e-3 * P.sum()
+
+
+def test_ba_transform_reproduces_training_points(golden):
+    import spateo_release_b200 as st
+
+    g = golden("3d_full_warp")
+    m = _model(g)
+    m.run()
+    XAHat, vel, opt = st.align.BA_transform(m.vecfld, g["raw_coords_moving"], device="0")
+    scale = np.abs(m.XAHat).max()
+    assert np.abs(XAHat - m.XAHat).max() < 2e-5 * scale
+    assert np.abs(opt - m.optimal_RnA).max() < 2e-5 * scale
+    # and against the oracle's evaluation of the same dictionary
+    oX, ov, oo = mo.ba_transform(m.vecfld, g["raw_coords_moving"], dtype="float64")
+    assert np.abs(XAHat - oX).max() < 1e-9 * scale + 1e-9
+    assert np.abs(vel - ov).max() < 1e-9 * scale + 1e-9
+
+
+def test_morpho_align_driver_and_gp_field(golden):
+    import spateo_release_b200 as st
+
+    g = golden("2d_full")
+    mov, fix = _adata_from_golden(g)
+    np.random.seed(0)
+    aligned, pis = st.align.morpho_align([fix, mov], device="0", verbose=False, SVI_mode=False, max_iter=100, mode="SN-N")
+    assert pis[0].shape == (fix.shape[0], mov.shape[0])
+    for k in ("align_spatial", "align_spatial_rigid", "align_spatial_nonrigid"):
+        assert k in aligned[1].obsm
+    assert "VecFld_morpho" in aligned[1].uns and "iter_spatial" in aligned[1].uns
+    assert len(aligned[1].uns["iter_spatial"]["align_spatial"]) == 100
+    assert not np.allclose(mov.obsm["spatial"], aligned[1].obsm["align_spatial"])  # inputs untouched, copy aligned
+    assert "align_spatial" not in mov.obsm
+    st.tdr.morphofield_gp(aligned[1], spatial_key="spatial", NX=np.asarray(mov.obsm["spatial"])[:10], device="0")
+    vf = aligned[1].uns["VecFld_morpho"]
+    want = mo.gp_velocity(np.asarray(mov.obsm["spatial"], dtype=float), vf)
+    assert np.abs(vf["V"] - want).max() < 1e-12 + 1e-9 * np.abs(want).max()
+    assert vf["grid_V"].shape == (10, 2) and vf["method"] == "gaussian_process"
+
+
+def test_error_behaviour():
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(60, 60, 8, dim=2)
+    with pytest.raises(KeyError):
+        st.align.Morpho_pairwise(A, B, spatial_key="missing", device="0")
+    with pytest.raises(ValueError):
+        st.align.Morpho_pairwise(A, B, dissimilarity="manhattan", device="0")
+    with pytest.raises(ValueError):
+        st.align.Morpho_pairwise(A, B, rep_layer="nolayer", device="0")
+    with pytest.raises(NotImplementedError):
+        st.align.Morpho_pairwise(A, B, kernel_type="tps", device="0")
+    C3, _ = make_slice_pair(60, 60, 8, dim=3)
+    with pytest.raises(AssertionError):
+        st.align.Morpho_pairwise(A, C3, device="0")
+
+
+def test_ragged_and_tiny_inputs():
+    """Sizes that do not divide any tile (rows 1025 -> two row tiles, 7 columns, K > unique points)."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(1025, 777, 9, dim=2, seed=5)
+    np.random.seed(0)
+    m = st.align.Morpho_pairwise(B, A, device="0", verbose=False, SVI_mode=False, max_iter=90, nn_init=False)
+    P = m.run()
+    np.random.seed(0)
+    o = mo.MorphoPairOracle(np.asarray(B.obsm["spatial"]), np.asarray(A.obsm["spatial"]), [m.exp_layers_A[0]],
+                            [m.exp_layers_B[0]], dtype="float64", SVI_mode=False, max_iter=90, nn_init=False)
+    o.run()
+    scale = np.abs(o.XAHat).max()
+    assert np.abs(m.XAHat - o.XAHat).max() / scale < 1e-3
+    assert np.abs(m.optimal_RnA - o.optimal_RnA).max() / scale < 1e-3
+    assert P.shape == (777, 1025)
+
+
+def test_large_pair_invariants():
+    """Size-independent properties at a size the oracle cannot reach quickly (20k x 18k, 3-D, K=64):
+    row/column accounting of the never-materialised P, proper rotation, monotone sigma2 floor."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(20000, 18000, 64, dim=3, seed=7, z_thickness=20.0)
+    np.random.seed(0)
+    m = st.align.Morpho_pairwise(B, A, device="0", verbose=False, SVI_mode=False, max_iter=85, K=64, nn_init=False,
+                                 materialize_P=False)
+    m.run()
+    Sp_rows, Sp_cols = float(m.K_NA.astype(np.float64).sum()), float(m.K_NB.astype(np.float64).sum())
+    assert abs(Sp_rows - Sp_cols) < 1e-4 * Sp_rows, "sum_i K_NA must equal sum_j K_NB (two independent reductions)"
+    assert np.all(m.K_NB <= 1.0 + 1e-5)
+    R = m.optimal_R.astype(np.float64)
+    assert np.abs(R @ R.T - np.eye(3)).max() < 1e-5 and abs(np.linalg.det(R) - 1) < 1e-5
+    assert np.isfinite(m.XAHat).all() and float(m.sigma2) >= 1e-3
+    # the recovered rigid motion maps B back onto A: residual small compared with the slice extent
+    assert m.trace[-1, 0] < m.trace[0, 0]

@@ -1,0 +1,113 @@
+"""CPU tests: C-ABI exports, header/ctypes agreement and the host-side helpers against the oracle."""
+
+import numpy as np
+import pytest
+
+from oracle import morpho_oracle as mo
+from spateo_release_b200 import _capi
+from spateo_release_b200.alignment import utils as U
+from spateo_release_b200.alignment.morpho_alignment import compose_transformations
+from spateo_release_b200.synthetic import make_slice_pair
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__ as g
+
+    g.build()
+    lib = _capi.load_library()
+    names = _capi.declared_functions()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in lib._spb_signatures, f"{n} has no ctypes signature"
+    assert lib.spb_version() >= 100
+    assert lib.spb_sizeof_em_params() == _capi.C.sizeof(_capi.SpbEmParams)
+    assert lib.spb_sizeof_scalars() == _capi.C.sizeof(_capi.SpbScalars)
+
+
+def test_no_oracle_import_in_product():
+    import os
+    import re
+
+    root = os.path.join(_capi.REPO_ROOT, "spateo_release_b200")
+    for dp, _, fs in os.walk(root):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f"{f} imports the oracle"
+
+
+def test_voxel_data_matches_reference_loop():
+    rng = np.random.default_rng(0)
+    for D, n in ((2, 1500), (3, 900)):
+        coords = rng.uniform(0, 50, size=(n, D)).astype(np.float32)
+        ge = rng.poisson(1.0, size=(n, 17)).astype(np.float32)
+        c_ref, g_ref = mo.voxel_data(coords, ge, voxel_num=max(min(int(n / 20), 1000), 100))
+        c_new, g_new = U.voxel_data(coords, ge, voxel_num=max(min(int(n / 20), 1000), 100))
+        assert c_ref.shape == c_new.shape and np.array_equal(c_ref, c_new)
+        assert np.abs(g_ref - g_new).max() < 1e-5
+
+
+def test_inlier_from_NN_matches_oracle():
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(400, 2))
+    th = 0.4
+    R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    y = x @ R.T + 0.3 + rng.normal(0, 0.02, size=x.shape)
+    y[:40] = rng.normal(size=(40, 2)) * 3
+    d = rng.uniform(0, 1, size=(400, 1))
+    a = mo.inlier_from_NN(x, y, d)
+    b = U.inlier_from_NN(x, y, d)
+    for u, v in zip(a, b):
+        assert np.allclose(u, v, rtol=1e-9, atol=1e-12)
+
+
+def test_normalize_coords_matches_oracle():
+    rng = np.random.default_rng(2)
+    a = rng.uniform(0, 100, size=(300, 3)).astype(np.float32)
+    b = rng.uniform(10, 80, size=(280, 3)).astype(np.float32)
+    ca, cb, sc, mu = U.normalize_coords(a, b)
+    oa, ob, osc, omu = mo.normalize_coords(a, b)
+    assert np.abs(ca - oa).max() < 1e-5 and np.abs(cb - ob).max() < 1e-5
+    assert np.allclose(sc, osc, rtol=1e-6) and np.allclose(mu, omu, rtol=1e-6)
+    assert a[0, 0] != ca[0, 0]  # inputs are not mutated
+
+
+def test_check_spatial_coords_errors():
+    A, _ = make_slice_pair(50, 50, 5, dim=2)
+    with pytest.raises(KeyError):
+        U.check_spatial_coords(A, "nope")
+    A.obsm["flat"] = np.c_[np.arange(50.0), np.zeros(50)]
+    with pytest.raises(ValueError):
+        U.check_spatial_coords(A, "flat")
+    A.obsm["xyz0"] = np.c_[A.obsm["spatial"], np.zeros(50)]
+    assert U.check_spatial_coords(A, "xyz0").shape == (50, 2)  # constant axis dropped
+
+
+def test_common_genes_and_errors():
+    assert U.intersect_lsts(["a", "b", "c"], ["c", "a"]) == ["a", "c"]
+    with pytest.raises(ValueError):
+        U.filter_common_genes(["a"], ["b"])
+
+
+def test_solve_RT_and_chain_composition():
+    rng = np.random.default_rng(3)
+    Y = rng.normal(size=(100, 2))
+    th = 0.7
+    R0 = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    X = Y @ R0.T + np.array([1.0, -2.0])
+    R, t = U.solve_RT_by_correspondence(X, Y)
+    assert np.allclose(Y @ R.T + t, X, atol=1e-9)
+    # composing two links equals applying them one after the other (morpho_alignment.py:300-303)
+    tr = [{"Rotation": R, "Translation": t}, {"Rotation": R0.T, "Translation": np.array([0.5, 0.5])}]
+    (R1, t1), (R2, t2) = compose_transformations(tr)
+    p = rng.normal(size=(5, 2))
+    step = (p @ tr[1]["Rotation"].T + tr[1]["Translation"]) @ tr[0]["Rotation"].T + tr[0]["Translation"]
+    assert np.allclose(p @ R2.T + t2, step)
+
+
+def test_label_transfer_defaults():
+    d = U.generate_label_transfer_dict(["x", "y"], ["x", "z"])
+    assert abs(sum(d["x"].values()) - 1) < 1e-6 and d["x"]["x"] > d["x"]["z"]
+    with pytest.raises(KeyError):
+        U.check_label_transfer_dict(["x"], ["x", "q"], {"x": {"x": 1.0}})
