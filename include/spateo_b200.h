@@ -114,8 +114,8 @@ typedef struct spb_em_params {
   float* PXB;                  /* [3][ldx] rows of P @ XB */
   float* PXB_term;             /* [3][ldx] (SVI running average) */
   float* K_NB;                 /* [NBb] */
-  float* colgeom;              /* [nbb_pad][4] coordinates of this iteration's columns */
-  float* colconst;             /* [nbb_pad][8] (y0,y1,y2,a_j, b_j,c_j,0,0) */
+  float* colgeom;              /* [nbb_pad][8] (y0,y0,y1,y1,y2,y2,0,0): this iteration's columns, duplicated for f32x2 */
+  float* colconst;             /* [nbb_pad][16] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, 0,0,0,0); zero beyond NBb */
   float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
   float* rowpart;              /* [seg2][8][ldx] partial row statistics */
   double* UtWU;                /* [K][K] accumulator */

@@ -583,8 +583,8 @@ class Morpho_pairwise:
         s["PXB"] = torch.zeros((3, ldx), dtype=f32, device=dev)
         s["PXB_term"] = torch.zeros((3, ldx), dtype=f32, device=dev)
         s["K_NB"] = torch.zeros((self._nbb_pad,), dtype=f32, device=dev)
-        s["colgeom"] = torch.zeros((self._nbb_pad, 4), dtype=f32, device=dev)
-        s["colconst"] = torch.zeros((self._nbb_pad, 8), dtype=f32, device=dev)
+        s["colgeom"] = torch.zeros((self._nbb_pad, 8), dtype=f32, device=dev)
+        s["colconst"] = torch.zeros((self._nbb_pad, 16), dtype=f32, device=dev)
         s["colpart"] = torch.zeros((nrb, 4, self._nbb_pad), dtype=f32, device=dev)
         seg1 = self._choose_segments(nrb, nbb)
         seg2 = self._choose_segments(nrb, nbb)

@@ -6,6 +6,8 @@
 //   col_finalize   turns them into the per-column constants a_j, b_j, c_j (and K_NB_j).
 //   sweep 2  streams GT again and accumulates, per moving cell i (thread-owned registers), K_NA_spatial, K_NA_sigma2,
 //            sum_j Psigma d, K_NA and the D components of P @ XB.
+//   All pair arithmetic is packed fp32x2 (FADD2/FMUL2/FFMA2): the v1 scalar kernels were issue-bound at 22 instructions
+//   per cell pair (profiles/ncu_estep_r01_v1_summary.md).
 //   row_finalize   reduces the per-segment partials in fp64 and forms the global sums.
 //
 // Algorithmic HBM traffic: 4 bytes per cell pair per sweep (the fp32 g_ij), 8 B/pair/iteration in total.
@@ -23,36 +25,80 @@ constexpr int kThreads = kConsumers + 32;
 
 struct __align__(16) SmemLayout {
   float tile[kStages][kColStage][kRowTile];  // 3 x 32 KB
-  float4 cols[kStages][kColStage][2];        // per-column constants (sweep 1 uses only [.][.][0])
+  float4 cols[kStages][kColStage][4];        // per-column constants, pre-duplicated for packed math (64 B / column)
   float red[2][kConsumers / 32][32];         // sweep-1 cross-warp staging
   uint64_t full[kStages];
   uint64_t empty[kStages];
 };
 
+// One stage = kColStage GT rows (4 KB each) + the columns' constants. Segments are multiples of kColStage columns, so
+// only the final stage of the whole matrix can be ragged: its missing columns re-read the last valid GT row and take
+// all-zero constants (the constant arrays are zero-padded), which keeps the consumer loops branch-free.
 __device__ __forceinline__ void producer_loop(SmemLayout& sm, const float* __restrict__ GT, int64_t ldx,
                                               const int32_t* __restrict__ col_index, const float* __restrict__ colsrc,
-                                              int col_floats, int i0, int j_begin, int j_end, int lane) {
+                                              int col_floats, int i0, int j_begin, int j_end, int NBb, int lane) {
   const int nst = (j_end - j_begin + kColStage - 1) / kColStage;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     if (st >= kStages) mbar_wait(&sm.empty[s], ((st / kStages) - 1) & 1);
     const int jb = j_begin + st * kColStage;
-    const int ncol = min(kColStage, j_end - jb);
-    if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)(ncol * kRowTile * 4 + ncol * col_floats * 4));
+    if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)(kColStage * kRowTile * 4 + kColStage * col_floats * 4));
     __syncwarp();
-    if (lane < ncol) {
-      const int j = jb + lane;
+    if (lane < kColStage) {
+      const int j = min(jb + lane, NBb - 1);
       const int64_t row = col_index ? (int64_t)col_index[j] : (int64_t)j;
       bulk_g2s(&sm.tile[s][lane][0], GT + row * ldx + i0, kRowTile * 4, &sm.full[s]);
-    }
-    // per-column constants: sweep 2 reads [ncol][8] floats in one copy; sweep 1 reads one float4 per column into the
-    // first slot of cols[][2]
-    if (col_floats == 8) {
-      if (lane == 0) bulk_g2s(&sm.cols[s][0][0], colsrc + (int64_t)jb * 8, ncol * 32, &sm.full[s]);
-    } else {
-      if (lane < ncol) bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)(jb + lane) * 4, 16, &sm.full[s]);
+      if (col_floats == 16) {
+        if (lane == 0) bulk_g2s(&sm.cols[s][0][0], colsrc + (int64_t)jb * 16, kColStage * 64, &sm.full[s]);
+      } else {
+        bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)(jb + lane) * 8, 32, &sm.full[s]);
+      }
     }
   }
+}
+
+// ---- packed fp32x2 arithmetic (Blackwell FADD2 / FMUL2 / FFMA2): two moving cells per instruction ------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+  u64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 ex2_2(u64 v) {
+  float a, b;
+  upk(v, a, b);
+  return pk(ex2f(a), ex2f(b));
+}
+__device__ __forceinline__ float hsum(u64 v) {
+  float a, b;
+  upk(v, a, b);
+  return a + b;
+}
+// squared distance of two moving cells (packed) to one fixed cell whose coordinates are pre-duplicated (y,y)
+__device__ __forceinline__ u64 sqdist2(u64 x0, u64 x1, u64 x2, u64 y0, u64 y1, u64 y2) {
+  const u64 d0 = sub2(x0, y0), d1 = sub2(x1, y1), d2 = sub2(x2, y2);
+  return fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
 }
 
 __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const float4& y) {
@@ -86,42 +132,39 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   __syncthreads();
 
   if (warp == kConsumers / 32) {
-    producer_loop(sm, GT, ldx, col_index, colgeom, 4, i0, j_begin, j_end, lane);
+    producer_loop(sm, GT, ldx, col_index, colgeom, 8, i0, j_begin, j_end, NBb, lane);
     return;
   }
-  // ---- consumers ----
-  const float c_q = sc->c_q, c_s = sc->c_s;
+  // ---- consumers: 4 rows per thread = 2 packed row pairs ----
+  const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
   const int r = i0 + tid * 4;
   const float4 X0 = *reinterpret_cast<const float4*>(XA + r);
   const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + r);
   const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + r);
   const float4 LM = *reinterpret_cast<const float4*>(lm + r);
   const float4 MM = *reinterpret_cast<const float4*>(mm + r);
+  const u64 xa0 = pk(X0.x, X0.y), xb0 = pk(X0.z, X0.w), xa1 = pk(X1.x, X1.y), xb1 = pk(X1.z, X1.w);
+  const u64 xa2 = pk(X2.x, X2.y), xb2 = pk(X2.z, X2.w);
+  const u64 lma = pk(LM.x, LM.y), lmb = pk(LM.z, LM.w), mma = pk(MM.x, MM.y), mmb = pk(MM.z, MM.w);
   const int nst = (j_end - j_begin + kColStage - 1) / kColStage;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     mbar_wait(&sm.full[s], (st / kStages) & 1);
     const int jb = j_begin + st * kColStage;
-    const int ncol = min(kColStage, j_end - jb);
     float acc[32];  // index v * 8 + jj
 #pragma unroll
-    for (int q = 0; q < 32; ++q) acc[q] = 0.f;
-#pragma unroll
     for (int jj = 0; jj < kColStage; ++jj) {
-      if (jj < ncol) {
-        const float4 y = sm.cols[s][jj][0];
-        const float4 g = *reinterpret_cast<const float4*>(&sm.tile[s][jj][tid * 4]);
-        float d, sv, qm, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f;
-        d = sqdist(X0.x, X1.x, X2.x, y); sv = ex2f(c_s * d); qm = ex2f(fmaf(c_q, d, LM.x));
-        c1 += sv; c2 = fmaf(sv, MM.x, c2); c3 += qm; c4 = fmaf(qm, g.x, c4);
-        d = sqdist(X0.y, X1.y, X2.y, y); sv = ex2f(c_s * d); qm = ex2f(fmaf(c_q, d, LM.y));
-        c1 += sv; c2 = fmaf(sv, MM.y, c2); c3 += qm; c4 = fmaf(qm, g.y, c4);
-        d = sqdist(X0.z, X1.z, X2.z, y); sv = ex2f(c_s * d); qm = ex2f(fmaf(c_q, d, LM.z));
-        c1 += sv; c2 = fmaf(sv, MM.z, c2); c3 += qm; c4 = fmaf(qm, g.z, c4);
-        d = sqdist(X0.w, X1.w, X2.w, y); sv = ex2f(c_s * d); qm = ex2f(fmaf(c_q, d, LM.w));
-        c1 += sv; c2 = fmaf(sv, MM.w, c2); c3 += qm; c4 = fmaf(qm, g.w, c4);
-        acc[0 * 8 + jj] = c1; acc[1 * 8 + jj] = c2; acc[2 * 8 + jj] = c3; acc[3 * 8 + jj] = c4;
-      }
+      const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
+      const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (0,0)
+      const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+      const u64 da = sqdist2(xa0, xa1, xa2, ya.x, ya.y, yb.x);
+      const u64 db = sqdist2(xb0, xb1, xb2, ya.x, ya.y, yb.x);
+      const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+      const u64 qa = ex2_2(fma2(CQ, da, lma)), qb = ex2_2(fma2(CQ, db, lmb));
+      acc[0 * 8 + jj] = hsum(add2(sa, sb));
+      acc[1 * 8 + jj] = hsum(fma2(sa, mma, mul2(sb, mmb)));
+      acc[2 * 8 + jj] = hsum(add2(qa, qb));
+      acc[3 * 8 + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // stage buffer is free again
@@ -144,7 +187,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
 #pragma unroll
       for (int w = 0; w < kConsumers / 32; ++w) t += sm.red[buf][w][lane];
       const int v = lane >> 3, jj = lane & 7;
-      if (jj < ncol) colpart[((int64_t)rb * 4 + v) * nbb_pad + jb + jj] = t;
+      if (jb + jj < j_end) colpart[((int64_t)rb * 4 + v) * nbb_pad + jb + jj] = t;
     }
   }
 }
@@ -167,10 +210,14 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
   const double a = 1.0 / (omega + C[1]);                     // utils.py:1059
   const double b = inl / (C[2] + 1e-8);                      // utils.py:1073
   const double c = inl / (C[3] + 1e-8);                      // utils.py:1083
-  const float4 y = *reinterpret_cast<const float4*>(colgeom + (int64_t)j * 4);
-  float4* out = reinterpret_cast<float4*>(colconst + (int64_t)j * 8);
-  out[0] = make_float4(y.x, y.y, y.z, (float)a);
-  out[1] = make_float4((float)b, (float)c, 0.f, 0.f);
+  const float* yg = colgeom + (int64_t)j * 8;  // (y0,y0,y1,y1,y2,y2,0,0)
+  const float y0 = yg[0], y1 = yg[2], y2 = yg[4];
+  const float af = (float)a, bf = (float)b, cf = (float)c;
+  float4* out = reinterpret_cast<float4*>(colconst + (int64_t)j * 16);
+  out[0] = make_float4(y0, y0, y1, y1);
+  out[1] = make_float4(y2, y2, af, af);
+  out[2] = make_float4(bf, bf, cf, cf);
+  out[3] = make_float4(0.f, 0.f, 0.f, 0.f);
   K_NB[j] = (float)(c * C[3]);                                // column sum of P (morpho_class.py:1176)
 }
 
@@ -197,56 +244,69 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   }
   __syncthreads();
   if (warp == kConsumers / 32) {
-    if (j_begin < j_end) producer_loop(sm, GT, ldx, col_index, colconst, 8, i0, j_begin, j_end, lane);
+    if (j_begin < j_end) producer_loop(sm, GT, ldx, col_index, colconst, 16, i0, j_begin, j_end, NBb, lane);
     return;
   }
-  const float c_q = sc->c_q, c_s = sc->c_s;
+  const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
   const int r = i0 + tid * 4;
   const float4 X0 = *reinterpret_cast<const float4*>(XA + r);
   const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + r);
   const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + r);
   const float4 LM = *reinterpret_cast<const float4*>(lm + r);
-  float4 a_sp = make_float4(0, 0, 0, 0), a_s2 = a_sp, a_sd = a_sp, a_k = a_sp, px = a_sp, py = a_sp, pz = a_sp;
+  const u64 xa0 = pk(X0.x, X0.y), xb0 = pk(X0.z, X0.w), xa1 = pk(X1.x, X1.y), xb1 = pk(X1.z, X1.w);
+  const u64 xa2 = pk(X2.x, X2.y), xb2 = pk(X2.z, X2.w);
+  const u64 lma = pk(LM.x, LM.y), lmb = pk(LM.z, LM.w);
+  const u64 Z = pk(0.f, 0.f);
+  // accumulators: [row pair a | b] x {K_NA_spatial/m, K_NA_sigma2, sum Psigma d, K_NA, (P@XB)_x, _y, _z}
+  u64 spa = Z, spb = Z, s2a = Z, s2b = Z, sda = Z, sdb = Z, ka = Z, kb = Z, pxa = Z, pxb = Z, pya = Z, pyb = Z, pza = Z, pzb = Z;
   const int nst = j_begin < j_end ? (j_end - j_begin + kColStage - 1) / kColStage : 0;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     mbar_wait(&sm.full[s], (st / kStages) & 1);
-    const int ncol = min(kColStage, j_end - (j_begin + st * kColStage));
 #pragma unroll
     for (int jj = 0; jj < kColStage; ++jj) {
-      if (jj < ncol) {
-        const float4 ya = sm.cols[s][jj][0];  // y0 y1 y2 a_j
-        const float4 bc = sm.cols[s][jj][1];  // b_j c_j
-        const float4 g = *reinterpret_cast<const float4*>(&sm.tile[s][jj][tid * 4]);
-        float d, sv, qm, t, p;
-#define SPB_ROW(C)                                                     \
-  d = sqdist(X0.C, X1.C, X2.C, ya);                                    \
-  sv = ex2f(c_s * d);                                                  \
-  qm = ex2f(fmaf(c_q, d, LM.C));                                       \
-  a_sp.C = fmaf(sv, ya.w, a_sp.C);                                     \
-  t = qm * bc.x;                                                       \
-  a_s2.C += t;                                                         \
-  a_sd.C = fmaf(t, d, a_sd.C);                                         \
-  p = (qm * g.C) * bc.y;                                               \
-  a_k.C += p;                                                          \
-  px.C = fmaf(p, ya.x, px.C);                                          \
-  py.C = fmaf(p, ya.y, py.C);                                          \
-  pz.C = fmaf(p, ya.z, pz.C);
-        SPB_ROW(x) SPB_ROW(y) SPB_ROW(z) SPB_ROW(w)
-#undef SPB_ROW
-      }
+      const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
+      const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
+      const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
+      const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+      const u64 da = sqdist2(xa0, xa1, xa2, c0.x, c0.y, c1.x);
+      const u64 db = sqdist2(xb0, xb1, xb2, c0.x, c0.y, c1.x);
+      const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+      const u64 qa = ex2_2(fma2(CQ, da, lma)), qb = ex2_2(fma2(CQ, db, lmb));
+      spa = fma2(sa, c1.y, spa);
+      spb = fma2(sb, c1.y, spb);
+      const u64 ta = mul2(qa, c2.x), tb = mul2(qb, c2.x);
+      s2a = add2(s2a, ta);
+      s2b = add2(s2b, tb);
+      sda = fma2(ta, da, sda);
+      sdb = fma2(tb, db, sdb);
+      const u64 pa = mul2(mul2(qa, g.x), c2.y), pb = mul2(mul2(qb, g.y), c2.y);
+      ka = add2(ka, pa);
+      kb = add2(kb, pb);
+      pxa = fma2(pa, c0.x, pxa);
+      pxb = fma2(pb, c0.x, pxb);
+      pya = fma2(pa, c0.y, pya);
+      pyb = fma2(pb, c0.y, pyb);
+      pza = fma2(pa, c1.x, pza);
+      pzb = fma2(pb, c1.x, pzb);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);
   }
   float* out = rowpart + ((int64_t)seg * 8) * ldx + r;
-  *reinterpret_cast<float4*>(out + 0 * ldx) = a_sp;
-  *reinterpret_cast<float4*>(out + 1 * ldx) = a_s2;
-  *reinterpret_cast<float4*>(out + 2 * ldx) = a_sd;
-  *reinterpret_cast<float4*>(out + 3 * ldx) = a_k;
-  *reinterpret_cast<float4*>(out + 4 * ldx) = px;
-  *reinterpret_cast<float4*>(out + 5 * ldx) = py;
-  *reinterpret_cast<float4*>(out + 6 * ldx) = pz;
+  auto st4 = [&](int q, u64 a, u64 b) {
+    float4 v;
+    upk(a, v.x, v.y);
+    upk(b, v.z, v.w);
+    *reinterpret_cast<float4*>(out + (int64_t)q * ldx) = v;
+  };
+  st4(0, spa, spb);
+  st4(1, s2a, s2b);
+  st4(2, sda, sdb);
+  st4(3, ka, kb);
+  st4(4, pxa, pxb);
+  st4(5, pya, pyb);
+  st4(6, pza, pzb);
 }
 
 // per row: fold the segment partials (fp64), write the fp32 statistics, accumulate the global sums
@@ -280,7 +340,10 @@ __global__ void gather_cols_kernel(const float* __restrict__ xb4, const int32_t*
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= NBb) return;
   const int64_t src = idx ? idx[j] : j;
-  reinterpret_cast<float4*>(colgeom)[j] = reinterpret_cast<const float4*>(xb4)[src];
+  const float4 y = reinterpret_cast<const float4*>(xb4)[src];
+  float4* out = reinterpret_cast<float4*>(colgeom + (int64_t)j * 8);
+  out[0] = make_float4(y.x, y.x, y.y, y.y);
+  out[1] = make_float4(y.z, y.z, 0.f, 0.f);
 }
 
 // dense P for the caller (utils.py:1083): P[i][j] = qm_ij g_ij c_j, transposed through shared memory
@@ -296,8 +359,9 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
     float p = 0.f;
     if (j < NBb && i < NA) {
       const int64_t row = col_index ? col_index[j] : j;
-      const float4 ya = *reinterpret_cast<const float4*>(colconst + (int64_t)j * 8);
-      const float cj = colconst[(int64_t)j * 8 + 5];
+      const float* cc = colconst + (int64_t)j * 16;
+      const float4 ya = make_float4(cc[0], cc[2], cc[4], 0.f);
+      const float cj = cc[10];
       const float d = sqdist(XA[i], XA[ldx + i], XA[2 * ldx + i], ya);
       p = ex2f(fmaf(c_q, d, lm[i])) * GT[row * ldx + i] * cj;
     }
