@@ -153,6 +153,8 @@ int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, in
                    int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:830 */
 
 /* ---- E-step: calc_distance(euc) + get_P_core + row/col sums, P never materialised ---------------------------- */
+/* pipeline shape of the two sweep kernels: 0 = 8 columns x 3 stages (2 CTAs/SM), 1 = 4 x 4 (3 CTAs/SM), 2 = 4 x 6 */
+int spb_set_sweep_config(int32_t cfg);
 int spb_gather_cols(const spb_em_params* p, int32_t iter, void* stream);   /* morpho_class.py:1149 */
 int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1049-1059,1063-1073,1080-1083 (column sums) */
 int spb_col_finalize(const spb_em_params* p, void* stream);               /* utils.py:1053-1055 + denominators */

@@ -112,6 +112,7 @@ def load_library():
         "spb_rows_normalize": ([P, I64, I64, I64, P, I64, P], C.c_int),
         "spb_gene_cost": ([P, I64, P, P, I64, P, I64, I64, I64, I32, I32, F, I32, P, I64, P], C.c_int),
         "spb_label_cost": ([P, P, P, I32, I64, I64, I32, P, I64, P], C.c_int),
+        "spb_set_sweep_config": ([I32], C.c_int),
         "spb_gather_cols": ([EP, I32, P], C.c_int),
         "spb_estep_sweep1": ([EP, I32, P], C.c_int),
         "spb_col_finalize": ([EP, P], C.c_int),

@@ -18,13 +18,13 @@
 namespace {
 
 constexpr int kRowTile = SPB_ROW_TILE;   // 1024 rows per CTA
-constexpr int kColStage = SPB_COL_STAGE; // 8 columns per stage
-constexpr int kStages = SPB_STAGES;
 constexpr int kConsumers = SPB_THREADS;  // 256
 constexpr int kThreads = kConsumers + 32;
 
-struct __align__(16) SmemLayout {
-  float tile[kStages][kColStage][kRowTile];  // 3 x 32 KB
+// Pipeline shape: kColStage columns per stage, kStages stages (compile-time variants, chosen by spb_set_sweep_config).
+template <int kColStage, int kStages>
+struct __align__(16) SmemLayoutT {
+  float tile[kStages][kColStage][kRowTile];  // kColStage x 4 KB per stage
   float4 cols[kStages][kColStage][4];        // per-column constants, pre-duplicated for packed math (64 B / column)
   float red[2][kConsumers / 32][32];         // sweep-1 cross-warp staging
   uint64_t full[kStages];
@@ -34,7 +34,8 @@ struct __align__(16) SmemLayout {
 // One stage = kColStage GT rows (4 KB each) + the columns' constants. Segments are multiples of kColStage columns, so
 // only the final stage of the whole matrix can be ragged: its missing columns re-read the last valid GT row and take
 // all-zero constants (the constant arrays are zero-padded), which keeps the consumer loops branch-free.
-__device__ __forceinline__ void producer_loop(SmemLayout& sm, const float* __restrict__ GT, int64_t ldx,
+template <int kColStage, int kStages>
+__device__ __forceinline__ void producer_loop(SmemLayoutT<kColStage, kStages>& sm, const float* __restrict__ GT, int64_t ldx,
                                               const int32_t* __restrict__ col_index, const float* __restrict__ colsrc,
                                               int col_floats, int i0, int j_begin, int j_end, int NBb, int lane) {
   const int nst = (j_end - j_begin + kColStage - 1) / kColStage;
@@ -101,6 +102,31 @@ __device__ __forceinline__ u64 sqdist2(u64 x0, u64 x1, u64 x2, u64 y0, u64 y1, u
   return fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
 }
 
+// Butterfly transpose-reduce: NV (= 32 or 16) per-lane values are summed across the 32 lanes of a warp in
+// (NV - 1) + log2(32 / NV) shuffles; afterwards acc[0] of lane l holds the warp total of value (l * NV / 32).
+template <int N, int OFF, int NV>
+__device__ __forceinline__ void bfly_step(float (&acc)[NV], int lane) {
+  if constexpr (N >= 1) {
+    const bool up = (lane & OFF) != 0;
+#pragma unroll
+    for (int q = 0; q < N; ++q) {
+      const float mine = up ? acc[q + N] : acc[q];
+      const float theirs = up ? acc[q] : acc[q + N];
+      acc[q] = mine + __shfl_xor_sync(0xffffffffu, theirs, OFF);
+    }
+  } else {
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], OFF);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void butterfly_reduce(float (&acc)[NV], int lane) {
+  bfly_step<NV / 2, 16, NV>(acc, lane);
+  bfly_step<NV / 4, 8, NV>(acc, lane);
+  bfly_step<NV / 8, 4, NV>(acc, lane);
+  bfly_step<NV / 16, 2, NV>(acc, lane);
+  bfly_step<NV / 32, 1, NV>(acc, lane);
+}
+
 __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const float4& y) {
   const float d0 = x0 - y.x, d1 = x1 - y.y, d2 = x2 - y.z;
   return fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
@@ -109,13 +135,15 @@ __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const floa
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 1: column sums
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kColStage, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colgeom, const float* __restrict__ XA, const float* __restrict__ lm,
                     const float* __restrict__ mm, const spb_scalars* __restrict__ sc, float* __restrict__ colpart,
                     int NBb, int nbb_pad, int cols_per_seg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  using Smem = SmemLayoutT<kColStage, kStages>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
@@ -132,7 +160,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   __syncthreads();
 
   if (warp == kConsumers / 32) {
-    producer_loop(sm, GT, ldx, col_index, colgeom, 8, i0, j_begin, j_end, NBb, lane);
+    producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, colgeom, 8, i0, j_begin, j_end, NBb, lane);
     return;
   }
   // ---- consumers: 4 rows per thread = 2 packed row pairs ----
@@ -151,7 +179,8 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     const int s = st % kStages;
     mbar_wait(&sm.full[s], (st / kStages) & 1);
     const int jb = j_begin + st * kColStage;
-    float acc[32];  // index v * 8 + jj
+    constexpr int NV = 4 * kColStage;  // partial sums per thread per stage, index v * kColStage + jj
+    float acc[NV];
 #pragma unroll
     for (int jj = 0; jj < kColStage; ++jj) {
       const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
@@ -161,32 +190,23 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
       const u64 db = sqdist2(xb0, xb1, xb2, ya.x, ya.y, yb.x);
       const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
       const u64 qa = ex2_2(fma2(CQ, da, lma)), qb = ex2_2(fma2(CQ, db, lmb));
-      acc[0 * 8 + jj] = hsum(add2(sa, sb));
-      acc[1 * 8 + jj] = hsum(fma2(sa, mma, mul2(sb, mmb)));
-      acc[2 * 8 + jj] = hsum(add2(qa, qb));
-      acc[3 * 8 + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
+      acc[0 * kColStage + jj] = hsum(add2(sa, sb));
+      acc[1 * kColStage + jj] = hsum(fma2(sa, mma, mul2(sb, mmb)));
+      acc[2 * kColStage + jj] = hsum(add2(qa, qb));
+      acc[3 * kColStage + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // stage buffer is free again
-    // butterfly transpose-reduce: 31 shuffles reduce all 32 values across the warp; lane q ends with value q
-#pragma unroll
-    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-      const bool up = (lane & off) != 0;
-#pragma unroll
-      for (int q = 0; q < n; ++q) {
-        const float mine = up ? acc[q + n] : acc[q];
-        const float theirs = up ? acc[q] : acc[q + n];
-        acc[q] = mine + __shfl_xor_sync(0xffffffffu, theirs, off);
-      }
-    }
+    butterfly_reduce<NV>(acc, lane);
+    constexpr int kShift = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);  // lane -> value index
     const int buf = st & 1;
-    sm.red[buf][warp][lane] = acc[0];
+    if ((lane & ((1 << kShift) - 1)) == 0) sm.red[buf][warp][lane >> kShift] = acc[0];
     named_bar_sync(1, kConsumers);
-    if (warp == 0) {
+    if (warp == 0 && lane < NV) {
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < kConsumers / 32; ++w) t += sm.red[buf][w][lane];
-      const int v = lane >> 3, jj = lane & 7;
+      const int v = lane / kColStage, jj = lane % kColStage;
       if (jb + jj < j_end) colpart[((int64_t)rb * 4 + v) * nbb_pad + jb + jj] = t;
     }
   }
@@ -224,12 +244,14 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 2: row statistics
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+template <int kColStage, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                     const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int cols_per_seg) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  using Smem = SmemLayoutT<kColStage, kStages>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
@@ -244,7 +266,7 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   }
   __syncthreads();
   if (warp == kConsumers / 32) {
-    if (j_begin < j_end) producer_loop(sm, GT, ldx, col_index, colconst, 16, i0, j_begin, j_end, NBb, lane);
+    if (j_begin < j_end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, colconst, 16, i0, j_begin, j_end, NBb, lane);
     return;
   }
   const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
@@ -374,9 +396,44 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
   }
 }
 
+int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
+
+int cfg_cols() { return g_sweep_cfg == 0 ? 8 : 4; }
+
 int cols_per_segment(int NBb, int nseg) {
+  const int cs = cfg_cols();
   int c = (NBb + nseg - 1) / nseg;
-  return ((c + kColStage - 1) / kColStage) * kColStage;
+  return ((c + cs - 1) / cs) * cs;
+}
+
+template <int C, int S, int B>
+int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
+  using Smem = SmemLayoutT<C, S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(p->ldx / kRowTile, p->seg1);
+  estep_sweep1_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
+                                                                  p->colpart, p->NBb, p->nbb_pad, cols_per_segment(p->NBb, p->seg1));
+  return 0;
+}
+
+template <int C, int S, int B>
+int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
+  using Smem = SmemLayoutT<C, S>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  dim3 grid(p->ldx / kRowTile, p->seg2);
+  estep_sweep2_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
+                                                                  p->rowpart, p->NBb, cols_per_segment(p->NBb, p->seg2));
+  return 0;
 }
 
 }  // namespace
@@ -391,18 +448,18 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
   return 0;
 }
 
+extern "C" int spb_set_sweep_config(int32_t cfg) {
+  if (cfg < 0 || cfg > 2) return SPB_EINVAL;
+  g_sweep_cfg = cfg;
+  return 0;
+}
+
 extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayout));
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  const int nrb = p->ldx / kRowTile;
-  dim3 grid(nrb, p->seg1);
-  estep_sweep1_kernel<<<grid, kThreads, sizeof(SmemLayout), (cudaStream_t)stream>>>(
-      p->GT, p->ldx, batch_ptr(p, iter), p->colgeom, p->XAHat, p->lm, p->mm, p->sc, p->colpart, p->NBb, p->nbb_pad,
-      cols_per_segment(p->NBb, p->seg1));
+  int rc;
+  if (g_sweep_cfg == 1) rc = launch_sweep1<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_cfg == 2) rc = launch_sweep1<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else rc = launch_sweep1<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  if (rc) return rc;
   SPB_CHECK_LAUNCH();
   return 0;
 }
@@ -415,16 +472,11 @@ extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
 }
 
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLayout));
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  dim3 grid(p->ldx / kRowTile, p->seg2);
-  estep_sweep2_kernel<<<grid, kThreads, sizeof(SmemLayout), (cudaStream_t)stream>>>(
-      p->GT, p->ldx, batch_ptr(p, iter), p->colconst, p->XAHat, p->lm, p->sc, p->rowpart, p->NBb,
-      cols_per_segment(p->NBb, p->seg2));
+  int rc;
+  if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else rc = launch_sweep2<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  if (rc) return rc;
   SPB_CHECK_LAUNCH();
   return 0;
 }
