@@ -186,6 +186,16 @@ int spb_rbf_kernel_T(const float* x, int64_t n, int64_t ldx, const float* z, int
 int spb_field_eval(const double* q, int64_t n, int32_t D, const double* z, const double* Coff, int32_t K, double beta,
                    double* out, void* stream); /* transform.py:93,103; gaussian_process.py:109,117 */
 
+/* ---- SparseVFC building blocks (replaces third-party dynamo scVectorField.SparseVFC; parity unpinned) ---------- */
+/* UtWU[K][K] = U^T diag(w) U and UtX[K][3] = U^T X3 (fp64 accumulation; outputs are zeroed first) */
+int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_t K, const float* w, const float* X3,
+                      double* UtWU, double* UtX, void* stream); /* morpho_class.py:1266-1279; sparsevfc.py:189 (M-step) */
+/* V = U C, P_i inlier posterior (clamped at minP); Pf / PY3 are the fp32 weight and P*Y ([3][ldn]) for the gram call;
+   sums5 = {sum Ppre r, sum Ppre, sum P r, sum P, #{Ppre > theta}} */
+int spb_vfc_estep(const float* UT, int64_t ldn, int64_t N, int32_t M, int32_t D, const double* C, const double* Y,
+                  double sigma2, double gamma, double a, double minP, double theta, double* P, double* V, float* Pf,
+                  float* PY3, double* sums5, void* stream); /* sparsevfc.py:189-198 (dynamo get_P) */
+
 /* ---- host-buffer convenience (H2D/D2H inside; used for the end-to-end measurement) ------------------------------ */
 int spb_field_eval_host(const double* q_host, int64_t n, int32_t D, const double* z_host, const double* Coff_host,
                         int32_t K, double beta, double* out_host); /* transform.py:61-116 */

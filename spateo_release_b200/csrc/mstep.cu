@@ -81,7 +81,10 @@ __global__ void pxb_term_kernel(spb_em_params p) {
 // U^T diag(K_NA) U  and  U^T PXB_term : 32x32 output tiles, fp64 accumulation, atomics into the K x K accumulator.
 // grid.x = row chunks, grid.y = (kt, lt) tile pairs with kt <= lt.
 constexpr int kAccRows = 128;
-__global__ void __launch_bounds__(256) nonrigid_accumulate_kernel(spb_em_params p, int rows_per_block, int ntile) {
+__global__ void __launch_bounds__(256)
+weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const float* __restrict__ w,
+                     const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX,
+                     int rows_per_block, int ntile) {
   __shared__ float Uk[32][kAccRows + 1];
   __shared__ float Ul[32][kAccRows + 1];
   __shared__ float Xs[3][kAccRows];
@@ -98,12 +101,11 @@ __global__ void __launch_bounds__(256) nonrigid_accumulate_kernel(spb_em_params 
       q -= cnt;
     }
   }
-  const int K = p.K;
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   double acc[2][2] = {{0, 0}, {0, 0}};
-  double accx = 0.0;  // U^T PXB_term entry (threads < 96 of diagonal tiles)
+  double accx = 0.0;  // U^T X entry (threads < 96 of diagonal tiles)
   const int r_begin = blockIdx.x * rows_per_block;
-  const int r_end = min(p.NA, r_begin + rows_per_block);
+  const int r_end = min(N, r_begin + rows_per_block);
   for (int r0 = r_begin; r0 < r_end; r0 += kAccRows) {
     const int nr = min(kAccRows, r_end - r0);
     __syncthreads();
@@ -111,14 +113,14 @@ __global__ void __launch_bounds__(256) nonrigid_accumulate_kernel(spb_em_params 
       const int kk = q / kAccRows, rr = q % kAccRows;
       const int k = kt * 32 + kk, l = lt * 32 + kk;
       const bool ok = rr < nr;
-      const float w = ok ? p.K_NA[r0 + rr] : 0.f;
-      Uk[kk][rr] = (ok && k < K) ? p.UT[(int64_t)k * p.ldx + r0 + rr] : 0.f;
-      Ul[kk][rr] = (ok && l < K) ? p.UT[(int64_t)l * p.ldx + r0 + rr] * w : 0.f;
+      const float wv = ok ? w[r0 + rr] : 0.f;
+      Uk[kk][rr] = (ok && k < K) ? UT[(int64_t)k * ldx + r0 + rr] : 0.f;
+      Ul[kk][rr] = (ok && l < K) ? UT[(int64_t)l * ldx + r0 + rr] * wv : 0.f;
     }
     if (kt == lt) {
       for (int q = threadIdx.x; q < 3 * kAccRows; q += 256) {
         const int d = q / kAccRows, rr = q % kAccRows;
-        Xs[d][rr] = rr < nr ? p.PXB_term[(int64_t)d * p.ldx + r0 + rr] : 0.f;
+        Xs[d][rr] = rr < nr ? X3[(int64_t)d * ldx + r0 + rr] : 0.f;
       }
     }
     __syncthreads();
@@ -136,14 +138,50 @@ __global__ void __launch_bounds__(256) nonrigid_accumulate_kernel(spb_em_params 
     for (int b = 0; b < 2; ++b) {
       const int k = kt * 32 + 2 * ty + a, l = lt * 32 + 2 * tx + b;
       if (k < K && l < K) {
-        atomicAdd(&p.UtWU[(int64_t)k * K + l], acc[a][b]);
-        if (kt != lt) atomicAdd(&p.UtWU[(int64_t)l * K + k], acc[a][b]);
+        atomicAdd(&UtWU[(int64_t)k * K + l], acc[a][b]);
+        if (kt != lt) atomicAdd(&UtWU[(int64_t)l * K + k], acc[a][b]);
       }
     }
   if (kt == lt && threadIdx.x < 96) {
     const int k = kt * 32 + threadIdx.x / 3, d = threadIdx.x % 3;
-    if (k < K) atomicAdd(&p.UtPXB[k * 3 + d], accx);
+    if (k < K) atomicAdd(&UtX[k * 3 + d], accx);
   }
+}
+
+// SparseVFC E-step (dynamo scVectorField.SparseVFC get_P + bookkeeping; SURVEY.md Appendix E — parity unpinned):
+//   V_i = U_i C, r_i = |Y_i - V_i|^2, P_i = t1 / (t1 + t2), t1 = exp(-r / 2 sigma2), then the clamp to minP.
+// sums: [0] sum P_pre r  [1] sum P_pre  [2] sum P r  [3] sum P  [4] #{P > theta}
+__global__ void __launch_bounds__(128)
+vfc_estep_kernel(const float* __restrict__ UT, int64_t ldn, int N, int M, int D, const double* __restrict__ Cf,
+                 const double* __restrict__ Y, double sigma2, double t2, double minP, double theta,
+                 double* __restrict__ P, double* __restrict__ V, float* __restrict__ Pf, float* __restrict__ PY3,
+                 double* __restrict__ sums) {
+  double v[5] = {0, 0, 0, 0, 0};
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    double acc[3] = {0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+      const double u = (double)UT[(int64_t)m * ldn + i];
+      acc[0] += u * Cf[m * 3 + 0];
+      acc[1] += u * Cf[m * 3 + 1];
+      acc[2] += u * Cf[m * 3 + 2];
+    }
+    double r = 0.0, y[3] = {0, 0, 0};
+    for (int d = 0; d < D; ++d) {
+      y[d] = Y[(int64_t)i * D + d];
+      const double df = y[d] - acc[d];
+      r += df * df;
+      V[(int64_t)i * D + d] = acc[d];
+    }
+    const double t1 = exp(-r / (2.0 * sigma2));
+    const double ppre = t1 / (t1 + t2);
+    const double p = fmax(ppre, minP);
+    P[i] = p;
+    Pf[i] = (float)p;
+    for (int d = 0; d < 3; ++d) PY3[(int64_t)d * ldn + i] = d < D ? (float)(p * y[d]) : 0.f;
+    v[0] = ppre * r; v[1] = ppre; v[2] = p * r; v[3] = p; v[4] = ppre > theta ? 1.0 : 0.0;
+  }
+  block_reduce_atomic<5>(v, sums);
 }
 
 // SigmaInv = sigma2 lambda Gamma + U^T W U (SVI running average) (morpho_class.py:1266-1277)
@@ -520,7 +558,35 @@ extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
   const int npairs = ntile * (ntile + 1) / 2;
   int rows_per_block = 2048;
   dim3 grid((p->NA + rows_per_block - 1) / rows_per_block, npairs);
-  nonrigid_accumulate_kernel<<<grid, 256, 0, ST>>>(*p, rows_per_block, ntile);
+  weighted_gram_kernel<<<grid, 256, 0, ST>>>(p->UT, p->ldx, p->NA, p->K, p->K_NA, p->PXB_term, p->UtWU, p->UtPXB, rows_per_block, ntile);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_t K, const float* w, const float* X3,
+                                 double* UtWU, double* UtX, void* stream) {
+  cudaError_t e = cudaMemsetAsync(UtWU, 0, sizeof(double) * (size_t)K * K, ST);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(UtX, 0, sizeof(double) * (size_t)K * 3, ST);
+  if (e != cudaSuccess) return (int)e;
+  const int ntile = (K + 31) / 32;
+  const int npairs = ntile * (ntile + 1) / 2;
+  const int rows_per_block = 2048;
+  dim3 grid((unsigned)((N + rows_per_block - 1) / rows_per_block), npairs);
+  weighted_gram_kernel<<<grid, 256, 0, ST>>>(UT, ldx, (int)N, K, w, X3, UtWU, UtX, rows_per_block, ntile);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_vfc_estep(const float* UT, int64_t ldn, int64_t N, int32_t M, int32_t D, const double* C,
+                             const double* Y, double sigma2, double gamma, double a, double minP, double theta,
+                             double* P, double* V, float* Pf, float* PY3, double* sums5, void* stream) {
+  if (D < 1 || D > 3) return SPB_EINVAL;
+  cudaError_t e = cudaMemsetAsync(sums5, 0, sizeof(double) * 5, ST);
+  if (e != cudaSuccess) return (int)e;
+  const double t2 = pow(kTwoPi * sigma2, 0.5 * D) * (1.0 - gamma) / (gamma * a);
+  vfc_estep_kernel<<<(unsigned)((N + 127) / 128), 128, 0, ST>>>(UT, ldn, (int)N, M, D, C, Y, sigma2, t2, minP, theta, P, V,
+                                                                 Pf, PY3, sums5);
   SPB_CHECK_LAUNCH();
   return 0;
 }

@@ -1,0 +1,84 @@
+"""GPU: SparseVFC device solver against the float64 numpy restatement (oracle.sparse_vfc — parity unpinned vs dynamo)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import morpho_oracle as mo  # noqa: E402
+
+
+def _field_data(n, D, seed=0, outliers=0.1):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(0, 100, size=(n, D))
+    c = X - 50.0
+    V = np.zeros_like(X)
+    V[:, 0], V[:, 1] = -0.05 * c[:, 1], 0.05 * c[:, 0]  # rotation
+    V += 2.0 * np.exp(-np.sum(c**2, 1, keepdims=True) / (2 * 15.0**2)) * np.ones((1, D))  # bump
+    V += rng.normal(0, 0.1, size=V.shape)
+    k = int(outliers * n)
+    V[:k] = rng.uniform(-5, 5, size=(k, D))
+    return X, V
+
+
+@pytest.mark.parametrize("D,n,M", [(3, 6000, 60), (2, 4000, 33)])
+def test_sparsevfc_matches_oracle(D, n, M):
+    from spateo_release_b200.tdr.sparsevfc import SparseVFC
+
+    X, V = _field_data(n, D)
+    ctrl_idx = np.random.default_rng(1).permutation(n)[:M]
+    beta = 1.0 / 25.0**2
+    grid = X[:50] + 0.5
+    got = SparseVFC(X, V, Grid=grid, M=M, beta=beta, lambda_=0.02, MaxIter=40, ecr=0.0, ctrl_idx=ctrl_idx, device="0")
+    want = mo.sparse_vfc(X, V, ctrl_idx, beta, lambda_=0.02, MaxIter=40, ecr=0.0, Grid=grid)
+    assert got["iteration"] == want["iteration"] - 1
+    scale = np.abs(want["V"]).max()
+    assert np.abs(got["V"] - want["V"]).max() < 1e-4 * scale
+    assert np.abs(got["grid_V"] - want["grid_V"]).max() < 1e-4 * scale
+    assert abs(got["sigma2"] - want["sigma2"]) < 1e-4 * want["sigma2"]
+    assert np.abs(got["P"][:, 0] - want["P"]).max() < 1e-3
+    assert np.abs(got["E_traj"] - want["E_traj"]).max() < 1e-5 * np.abs(want["E_traj"]).max()
+    assert set(["X", "valid_ind", "X_ctrl", "ctrl_idx", "Y", "beta", "V", "C", "P", "VFCIndex", "sigma2", "grid", "grid_V",
+                "iteration", "tecr_traj", "E_traj"]) <= set(got)
+    # outliers are recognised
+    k = int(0.1 * n)
+    assert got["P"][:k, 0].mean() < 0.1 and got["P"][k:, 0].mean() > 0.5
+
+
+def test_morphofield_alias_and_restart_wrapper():
+    import spateo_release_b200 as st
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    X, V = _field_data(3000, 3, seed=3)
+    ad = AnnDataLite(np.zeros((3000, 2), dtype=np.float32), obsm={"align_spatial": X, "V_mapping": V})
+    assert st.tdr.morphofield is st.tdr.morphofield_sparsevfc
+    st.tdr.morphofield(ad, NX=X[:20], M=40, MaxIter=30, device="0")
+    vf = ad.uns["VecFld_morpho"]
+    assert vf["method"] == "sparsevfc" and vf["grid_V"].shape == (20, 3) and vf["V"].shape == (3000, 3)
+    ref, pred = vf["Y"], vf["V"]
+    cos = np.sum(ref * pred, 1) / (np.linalg.norm(ref, axis=1) * np.linalg.norm(pred, axis=1) + 1e-20)
+    assert np.median(cos[300:]) > 0.9
+
+
+def test_weighted_gram_matches_numpy():
+    import torch
+
+    from spateo_release_b200 import _capi
+    from spateo_release_b200._capi import check, ptr
+
+    lib = _capi.load_library()
+    rng = np.random.default_rng(0)
+    N, K, ld = 5000, 70, 5120
+    U = rng.uniform(0, 1, size=(K, N)).astype(np.float32)
+    w = rng.uniform(0, 1, size=N).astype(np.float32)
+    X3 = rng.normal(size=(3, N)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    UT = torch.zeros((K, ld), dtype=torch.float32, device=dev); UT[:, :N] = torch.from_numpy(U).to(dev)
+    wd = torch.zeros(ld, dtype=torch.float32, device=dev); wd[:N] = torch.from_numpy(w).to(dev)
+    Xd = torch.zeros((3, ld), dtype=torch.float32, device=dev); Xd[:, :N] = torch.from_numpy(X3).to(dev)
+    A = torch.empty((K, K), dtype=torch.float64, device=dev)
+    B = torch.empty((K, 3), dtype=torch.float64, device=dev)
+    check(lib.spb_weighted_gram(ptr(UT), ld, N, K, ptr(wd), ptr(Xd), ptr(A), ptr(B), _capi.current_stream_ptr()), "gram")
+    U64 = U.astype(np.float64)
+    assert np.abs(A.cpu().numpy() - (U64 * w.astype(np.float64)) @ U64.T).max() < 1e-9 * N
+    assert np.abs(B.cpu().numpy() - U64 @ X3.astype(np.float64).T).max() < 1e-9 * N
