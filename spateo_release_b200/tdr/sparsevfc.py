@@ -6,9 +6,11 @@ requirements.txt:7; call sites spateo/tdr/morphometrics/morphofield/sparsevfc.py
 by dynamo) and is checked against ``oracle.morpho_oracle.sparse_vfc`` only.
 
 Device work per EM iteration: ``spb_vfc_estep`` (V = U C, inlier posterior P, energy sums — one pass over U^T) and
-``spb_weighted_gram`` (U^T P U and U^T P Y, fp64 accumulation). The M x M normal equations are solved on the host with
-``scipy.linalg.lstsq`` exactly like the reference's ``lstsq_method="scipy"``; sigma^2 follows from the accumulated blocks
-(sum P|Y - UC|^2 = sum P|Y|^2 - 2 tr(C^T U^T P Y) + tr(C^T U^T P U C)), so U is streamed twice per iteration.
+``spb_weighted_gram`` (U^T P U and U^T P Y, fp64 accumulation). The M x M normal equations are solved on the device as the
+minimum-norm least-squares solution (symmetric eigen-decomposition with lstsq's eps*M singular-value cutoff — what the
+reference's ``lstsq_method="scipy"`` computes; both ``lstsq_method`` values map to it); sigma^2 follows from the accumulated
+blocks (sum P|Y - UC|^2 = sum P|Y|^2 - 2 tr(C^T U^T P Y) + tr(C^T U^T P U C)), so U is streamed twice per iteration and the
+host synchronises once per iteration (the convergence test of the reference needs the energy on the host).
 """
 
 from __future__ import annotations
@@ -16,7 +18,6 @@ from __future__ import annotations
 from typing import List, Optional, Tuple, Union
 
 import numpy as np
-import scipy.linalg
 import torch
 
 from .. import _capi
@@ -120,12 +121,13 @@ def SparseVFC(
         B_d = torch.empty((M, 3), dtype=torch.float64, device=dev)
         Cd = torch.zeros((M, 3), dtype=torch.float64, device=dev)
 
-        C = np.zeros((M, D))
+        Kd = torch.from_numpy(Kc).to(dev)
         sigma2 = max(float((Yv**2).sum() / (N * D)), 1e-7)
-        sumY2_w = None
         E, tecr, it = 1.0, 1.0, 0
         tecr_traj, E_traj = [], []
         Y2 = (Yd**2).sum(1)  # |Y_i|^2, reused for sum P |Y|^2
+        reg_energy = 0.0     # tr(C^T K C) of the current coefficients
+        rcond = np.finfo(np.float64).eps * M
         while it < MaxIter and tecr > ecr and sigma2 > 1e-8:
             E_old = E
             check(
@@ -134,23 +136,27 @@ def SparseVFC(
                 "spb_vfc_estep",
             )
             check(lib.spb_weighted_gram(ptr(UT), ldn, N, M, ptr(Pf), ptr(PY3), ptr(A_d), ptr(B_d), st), "spb_weighted_gram")
-            sumY2_w = float((P[:N] * Y2).sum().item())
-            s = sums.cpu().numpy()
-            A = A_d.cpu().numpy()
-            B = B_d.cpu().numpy()[:, :D]
-            E = s[0] / (2 * sigma2) + s[1] * np.log(sigma2) * D / 2 + lambda_ / 2 * np.trace(C.T @ Kc @ C)
+            # M-step on the device: minimum-norm solution of (lambda sigma2 K + U^T P U) C = U^T P Y through the symmetric
+            # eigen-decomposition with lstsq's singular-value cutoff (the reference calls scipy.linalg.lstsq, sparsevfc.py:189)
+            Areg = lambda_ * sigma2 * Kd + 0.5 * (A_d + A_d.T)
+            ev, Q = torch.linalg.eigh(Areg)
+            inv = torch.where(ev.abs() > rcond * ev.abs().max(), 1.0 / ev, torch.zeros_like(ev))
+            Cn = (Q * inv) @ (Q.T @ B_d)
+            stats = torch.stack([
+                (P[:N] * Y2).sum(), (Cn * B_d).sum(), (Cn * (A_d @ Cn)).sum(), (Cn * (Kd @ Cn)).sum(),
+            ])
+            s = torch.cat([sums, stats]).cpu().numpy()  # the one host synchronisation of the iteration
+            E = s[0] / (2 * sigma2) + s[1] * np.log(sigma2) * D / 2 + lambda_ / 2 * reg_energy
             tecr = abs((E - E_old) / E)
             tecr_traj.append(tecr)
             E_traj.append(E)
-            # M-step: (lambda sigma2 K + U^T P U) C = U^T P Y
-            C = scipy.linalg.lstsq(lambda_ * sigma2 * Kc + A, B)[0]
-            Cd.zero_()
-            Cd[:, :D] = torch.from_numpy(C).to(dev)
-            Sp = s[3]
-            resid = sumY2_w - 2.0 * np.trace(C.T @ B) + np.trace(C.T @ A @ C)
-            sigma2 = float(max(resid, 0.0) / (Sp * D))
+            Cd.copy_(Cn)
+            reg_energy = float(s[8])
+            resid = s[5] - 2.0 * s[6] + s[7]
+            sigma2 = float(max(resid, 0.0) / (s[3] * D))
             gamma = float(min(max(s[4] / N, 0.05), 0.95))
             it += 1
+        C = Cd[:, :D].cpu().numpy()
         # final field on the cells and on the grid
         check(
             lib.spb_vfc_estep(ptr(UT), ldn, N, M, D, ptr(Cd), ptr(Yd), max(sigma2, 1e-300), gamma, float(a), float(minP),
