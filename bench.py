@@ -207,6 +207,7 @@ def workload_config(args):
                     f"KL, {mode}, K={args.K}, nn_init=True, max_iter={args.max_iter}; one pair per GPU",
         "cells_per_slice": args.cells, "genes": args.genes, "dim": args.dim, "max_iter": args.max_iter, "K": args.K,
         "svi": bool(args.svi), "pairs_per_gpu": 1, "parallelism": "independent slice pair per GPU + 1 all-gather",
+        "zero_tile_culling": "on (product default; exact: skipped pairs are 0 in fp32) — dense timings under roofline.dense",
         "cache": "inputs_larger_than_L2 (cost matrix %.1f GB per pair)" % (4.0 * args.cells * args.cells / 1e9),
     }
 
@@ -353,35 +354,45 @@ def main():
         m.SVI_mode = bool(args.svi)
     e2e_sec = float(np.mean(e2e_times))
 
-    # ---- device-resident arm: EM loop only, cost matrix in HBM ----
-    sampler = ClockSampler(local_rank)
-    step_ms, sweep_ms = [], []
-    launches0 = 0
-    for s in range(args.warmup + args.steps):
-        m.reset_state()
-        ev = []
-        if s == args.warmup:
+    # ---- device-resident arms: EM loop only, cost matrix in HBM ----
+    # (1) product default: exact zero-tile culling on; (2) dense sweeps (culling off) for the plain 8 B/pair roofline
+    def timed_arm(cull, n_warm, n_steps, sample_clocks):
+        m.cull_zero_tiles = cull
+        sampler = ClockSampler(local_rank)
+        step_ms, sweep_ms, visited = [], [], []
+        launches0 = 0
+        for s in range(n_warm + n_steps):
+            m.reset_state()
+            ev = []
+            if s == n_warm:
+                barrier()
+                if sample_clocks:
+                    sampler.start()
+                launches0 = lib.spb_launch_count()
             barrier()
-            sampler.start()
-            launches0 = lib.spb_launch_count()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        m.run_em(sweep_events=ev)
-        consensus_step()
-        e1.record()
-        barrier()
-        if s >= args.warmup:
-            step_ms.append(max_over_ranks(e0.elapsed_time(e1)))
-            sweep_ms.append([(a.elapsed_time(b), c.elapsed_time(d)) for (a, b, c, d) in ev])
-    launches = lib.spb_launch_count() - launches0
-    clocks = sampler.stop()
-    ms_per_step = float(np.mean(step_ms))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m.run_em(sweep_events=ev)
+            consensus_step()
+            e1.record()
+            barrier()
+            if s >= n_warm:
+                step_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+                sweep_ms.append([(a.elapsed_time(b), c.elapsed_time(d)) for (a, b, c, d) in ev])
+                visited.append(m._state["trace_buf"][:, 7].cpu().numpy().copy())
+        launches = lib.spb_launch_count() - launches0
+        clocks = sampler.stop() if sample_clocks else None
+        return dict(ms=float(np.mean(step_ms)), sweeps=np.array(sweep_ms, dtype=np.float64), visited=np.array(visited),
+                    launches=int(launches), clocks=clocks)
+
+    main_arm = timed_arm(True, args.warmup, args.steps, True)
+    dense_arm = timed_arm(False, min(args.warmup, 1), max(1, min(args.steps, 2)), False)
+    m.cull_zero_tiles = True
+    ms_per_step = main_arm["ms"]
+    launches, clocks = main_arm["launches"], main_arm["clocks"]
     value = pairs_per_step * world / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernels (live CUDA-event timings of every launch in the timed region) ----
-    sw = np.array(sweep_ms, dtype=np.float64).reshape(-1, 2)
-    s1_ms, s2_ms = float(sw[:, 0].mean()), float(sw[:, 1].mean())
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -389,19 +400,44 @@ def main():
     except Exception:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = 4.0 * NA * cols  # one fp32 g_ij per cell pair per sweep
-    dom_ms = max(s1_ms, s2_ms)
+    nrb = m.ldx // 1024
+    tiles_all = float(nrb) * cols
+    # algorithmic bytes of one sweep launch = 4 B x (cell pairs the launch has to read): all pairs when dense, the visited
+    # (row block x column) tiles x N_A/nrb rows when culling skipped the provably-zero tiles
+    sw = main_arm["sweeps"]                                     # [steps, iters, 2] ms
+    vis = main_arm["visited"]                                   # [steps, iters] tiles
+    bytes_per_launch = 4.0 * vis * (float(NA) / nrb)            # [steps, iters]
+    s1_gbs = float(bytes_per_launch.sum() / (sw[..., 0].sum() * 1e-3) / 1e9)
+    s2_gbs = float(bytes_per_launch.sum() / (sw[..., 1].sum() * 1e-3) / 1e9)
+    dom = "estep_sweep2_kernel" if sw[..., 1].sum() >= sw[..., 0].sum() else "estep_sweep1_kernel"
+    dom_gbs = min(s1_gbs, s2_gbs)
+    dsw = dense_arm["sweeps"].reshape(-1, 2)
+    d1, d2 = float(dsw[:, 0].mean()), float(dsw[:, 1].mean())
+    alg_dense = 4.0 * NA * cols
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("cells") == args.cells and not args.svi:
+            traffic = tj.get(dom)
+    except Exception:
+        pass
     roofline = {
-        "bound": "hbm", "kernel": "estep_sweep2_kernel" if s2_ms >= s1_ms else "estep_sweep1_kernel",
-        "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
-        "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak_gbs,
+        "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": dom_gbs / peak_gbs,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-        "traffic": None,
-        "sweep1_ms": s1_ms, "sweep2_ms": s2_ms,
-        "sweep1_GBs": alg_bytes / (s1_ms * 1e-3) / 1e9, "sweep2_GBs": alg_bytes / (s2_ms * 1e-3) / 1e9,
-        "em_loop_GBs_8B_per_pair": 8.0 * pairs_per_step / (ms_per_step * 1e-3) / 1e9,
-        "em_loop_frac": 8.0 * pairs_per_step / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
-        "sweeps_share_of_step": (s1_ms + s2_ms) * args.max_iter / ms_per_step,
+        "traffic": traffic,
+        "definition": "sum over the timed launches of 4 B x cell pairs the launch must read (visited tiles) / sum of "
+                      "CUDA-event launch durations",
+        "sweep1_GBs": s1_gbs, "sweep2_GBs": s2_gbs,
+        "visited_pair_fraction": float(vis.sum() / (tiles_all * vis.size)),
+        "sweeps_share_of_step": float(sw.sum() / sw.shape[0] / ms_per_step),
+        "dense": {
+            "note": "same kernels with culling off: every launch reads all N_A x N_B pairs (4 B each)",
+            "value": pairs_per_step * world / (dense_arm["ms"] * 1e-3), "ms_per_step": dense_arm["ms"],
+            "sweep1_ms": d1, "sweep2_ms": d2, "sweep1_GBs": alg_dense / (d1 * 1e-3) / 1e9,
+            "sweep2_GBs": alg_dense / (d2 * 1e-3) / 1e9, "frac": alg_dense / (max(d1, d2) * 1e-3) / 1e9 / peak_gbs,
+            "em_loop_GBs_8B_per_pair": 8.0 * pairs_per_step / (dense_arm["ms"] * 1e-3) / 1e9,
+        },
     }
 
     if rank == 0:

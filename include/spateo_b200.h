@@ -61,6 +61,7 @@ typedef struct spb_scalars {
   double t[3];           /* (:1398-1402) */
   double dotKS;          /* sum_i K_NA_sigma2_i * SigmaDiag_i (:1427) */
   double sums[8];        /* scratch: Sp_spatial_new, Sp_sigma2_new, Sp_new, S2 */
+  double visited;        /* (row block, column) tiles visited by this iteration's sweeps (all of them without culling) */
   float c_q;             /* -log2(e) / (2 sigma2) */
   float c_s;             /* c_q * sigma2_variance */
   int32_t nonrigid_flag; /* latched once iter > nonrigid_start_iter (:289-291) */
@@ -83,6 +84,8 @@ typedef struct spb_em_params {
   int32_t seg2;                /* column segments of sweep 2 */
   int32_t nbb_pad;             /* pitch of the column-partial arrays */
   int32_t trace;               /* 1: record per-iteration scalars into trace_buf */
+  int32_t cull;                /* 1: drop (row block, column) tiles whose every pair underflows to exactly 0 */
+  int32_t reserved0;
   double lambdaVF;
   double gamma_a;
   double gamma_b;
@@ -118,6 +121,9 @@ typedef struct spb_em_params {
   float* colconst;             /* [nbb_pad][16] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, 0,0,0,0); zero beyond NBb */
   float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
   float* rowpart;              /* [seg2][8][ldx] partial row statistics */
+  float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
+  int32_t* collist;            /* [ldx/ROW_TILE][nbb_pad] per-row-block column work list */
+  int32_t* colcount;           /* [ldx/ROW_TILE] list lengths */
   double* UtWU;                /* [K][K] accumulator */
   double* UtPXB;               /* [K][3] accumulator */
   double* SigmaInv;            /* [K][K] (SVI running average) */
@@ -156,6 +162,8 @@ int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, in
 /* pipeline shape of the two sweep kernels: 0 = 8 columns x 3 stages (2 CTAs/SM), 1 = 4 x 4 (3 CTAs/SM), 2 = 4 x 6 */
 int spb_set_sweep_config(int32_t cfg);
 int spb_gather_cols(const spb_em_params* p, int32_t iter, void* stream);   /* morpho_class.py:1149 */
+/* row-block bounding boxes + per-block column work lists (exact zero-tile culling when p->cull) — new, no reference line */
+int spb_estep_col_lists(const spb_em_params* p, void* stream);
 int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1049-1059,1063-1073,1080-1083 (column sums) */
 int spb_col_finalize(const spb_em_params* p, void* stream);               /* utils.py:1053-1055 + denominators */
 int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1059-1083, morpho_class.py:1171-1176,1270,1357 */

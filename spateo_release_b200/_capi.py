@@ -114,6 +114,7 @@ def load_library():
         "spb_label_cost": ([P, P, P, I32, I64, I64, I32, P, I64, P], C.c_int),
         "spb_set_sweep_config": ([I32], C.c_int),
         "spb_gather_cols": ([EP, I32, P], C.c_int),
+        "spb_estep_col_lists": ([EP, P], C.c_int),
         "spb_estep_sweep1": ([EP, I32, P], C.c_int),
         "spb_col_finalize": ([EP, P], C.c_int),
         "spb_estep_sweep2": ([EP, I32, P], C.c_int),

@@ -42,6 +42,21 @@ def _round_up(x: int, m: int) -> int:
     return ((x + m - 1) // m) * m
 
 
+def morton_order(coords: np.ndarray) -> np.ndarray:
+    """Row permutation that sorts points along a Z-order curve (isotropic quantisation: 16 bits/axis in 2-D, 10 in 3-D)."""
+    c = np.asarray(coords, dtype=np.float64)
+    n, D = c.shape
+    bits = 16 if D == 2 else 10
+    lo = c.min(axis=0)
+    ext = max(float((c.max(axis=0) - lo).max()), 1e-30)
+    q = np.minimum(((c - lo) / ext * (2**bits - 1)).astype(np.uint64), np.uint64(2**bits - 1))
+    code = np.zeros(n, dtype=np.uint64)
+    for b in range(bits):
+        for d in range(D):
+            code |= ((q[:, d] >> np.uint64(b)) & np.uint64(1)) << np.uint64(b * D + d)
+    return np.argsort(code, kind="stable")
+
+
 def resolve_device(device) -> torch.device:
     """Reference semantics: "cpu" or a GPU index string (utils.py:35-66). Here every value maps to a CUDA device —
     there is no CPU path; ``CUDA_VISIBLE_DEVICES`` is NOT mutated (the reference does, utils.py:51)."""
@@ -103,8 +118,11 @@ class GeneCostBuilder:
 class Morpho_pairwise:
     """Align a moving slice ``sampleA`` onto a fixed slice ``sampleB`` (same constructor as morpho_class.py:110-167).
 
-    Extra keyword (not in the reference): ``materialize_P`` — when False ``run()`` skips building the dense
+    Extra keywords (not in the reference): ``materialize_P`` — when False ``run()`` skips building the dense
     N_A x N_B posterior (40 GB at 100k x 100k) and returns None; every other output is unaffected.
+    ``spatial_sort`` / ``cull_zero_tiles`` — the moving cells are processed in Morton order so that each 1024-row block is
+    spatially compact, and (row block, fixed cell) tiles whose every pair underflows to exactly 0 in fp32 are skipped;
+    results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
     Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
     ``pre_compute_dist``. Not implemented in this round (raise NotImplementedError): ``sparse_calculation_mode``,
     guidance pairs, ``kernel_type="geodist"``, ``dissimilarity="sym_kl"``.
@@ -168,6 +186,8 @@ class Morpho_pairwise:
         return_mapping: bool = False,
         update_R: bool = True,
         materialize_P: bool = True,
+        spatial_sort: bool = True,
+        cull_zero_tiles: bool = True,
     ) -> None:
         self.verbose = verbose
         self.sampleA, self.sampleB = sampleA, sampleB
@@ -198,6 +218,7 @@ class Morpho_pairwise:
         self.nonrigid_start_iter = nonrigid_start_iter
         self.return_mapping, self.update_R = return_mapping, update_R
         self.materialize_P = materialize_P
+        self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64
         self._check()
@@ -358,7 +379,8 @@ class Morpho_pairwise:
     @property
     def U(self) -> np.ndarray:
         """[N_A, K] kernel matrix as the reference exposes it."""
-        return self._UT[:, : self.NA].T.contiguous().cpu().numpy().astype(self._np_dtype)
+        u = self._UT[:, : self.NA].T.contiguous().cpu().numpy().astype(self._np_dtype)
+        return self._unsorted(u) if getattr(self, "_UT_is_sorted", False) else u
 
     # ------------------------------------------------------------------------------------------------------------------
     # device-side expression distances for small helper problems (coarse init, beta^2 init)
@@ -496,9 +518,28 @@ class Morpho_pairwise:
     # ------------------------------------------------------------------------------------------------------------------
     # device state
     # ------------------------------------------------------------------------------------------------------------------
+    def _set_row_order(self):
+        """Processing order of the moving cells (after the coarse initialisation moved them)."""
+        if self.spatial_sort and self.NA > _capi.ROW_TILE:
+            self._perm = morton_order(self.coordsA)
+            self._perm_dev = torch.from_numpy(self._perm).to(self._dev)
+        else:
+            self._perm, self._perm_dev = None, None
+
+    def _sorted(self, host_rows: np.ndarray) -> np.ndarray:
+        return host_rows if self._perm is None else host_rows[self._perm]
+
+    def _unsorted(self, sorted_rows: np.ndarray) -> np.ndarray:
+        if self._perm is None:
+            return sorted_rows
+        out = np.empty_like(sorted_rows)
+        out[self._perm] = sorted_rows
+        return out
+
     def _build_gene_cost(self):
         """GT[j][i] = prod_layers prob(metric(A_i, B_j)) (morpho_class.py:265-268 + utils.py:1080-1081)."""
         dev, lib = self._dev, self._lib
+        self._set_row_order()
         self._GT = torch.empty((self.NB, self.ldx), dtype=torch.float32, device=dev)
         gc = GeneCostBuilder(lib, dev)
         first = True
@@ -506,7 +547,7 @@ class Morpho_pairwise:
             self.exp_layers_A, self.exp_layers_B, self.dissimilarity, self.probability_type, self.probability_parameters
         ):
             if d_s == "label":
-                la = torch.from_numpy(np.ascontiguousarray(eA, dtype=np.int32)).to(dev)
+                la = torch.from_numpy(np.ascontiguousarray(eA if self._perm is None else eA[self._perm], dtype=np.int32)).to(dev)
                 lb = torch.from_numpy(np.ascontiguousarray(eB, dtype=np.int32)).to(dev)
                 LT = torch.from_numpy(np.ascontiguousarray(self.label_transfer, dtype=np.float32)).to(dev)
                 check(
@@ -516,6 +557,8 @@ class Morpho_pairwise:
                 )
             else:
                 A = self._to_device_pinned(eA)
+                if self._perm is not None:
+                    A = A.index_select(0, self._perm_dev)  # moving cells in Morton order
                 B = self._to_device_pinned(eB)
                 opA, rtA = gc.prepare(A, d_s, fixed=False)
                 opB, rtB = gc.prepare(B, d_s, fixed=True)
@@ -564,12 +607,16 @@ class Morpho_pairwise:
         self._nbb_pad = _round_up(nbb_alloc, 8) + 8
         s = {}
         s["xa"] = torch.zeros((3, ldx), dtype=f32, device=dev)
-        s["xa"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(self.coordsA.T, dtype=np.float32)).to(dev)
+        s["xa"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(self._sorted(self.coordsA).T, dtype=np.float32)).to(dev)
         s["xb4"] = torch.zeros((NB, 4), dtype=f32, device=dev)
         s["xb4"][:, :D] = torch.from_numpy(self.coordsB.astype(np.float32)).to(dev)
         s["Gamma"] = torch.from_numpy(np.ascontiguousarray(self.GammaSparse, dtype=np.float32)).to(dev)
         s["kappa"] = torch.ones((ldx,), dtype=f32, device=dev)
-        s["kappa"][:NA] = torch.from_numpy(self.kappa.astype(np.float32)).to(dev)
+        s["kappa"][:NA] = torch.from_numpy(self._sorted(self.kappa).astype(np.float32)).to(dev)
+        if self._perm is not None and not getattr(self, "_UT_is_sorted", False):
+            ut = torch.zeros_like(self._UT)
+            ut[:, :NA] = self._UT[:, :NA].index_select(1, self._perm_dev)
+            self._UT, self._UT_is_sorted = ut, True
         s["alpha"] = torch.ones((ldx,), dtype=f32, device=dev)
         s["SigmaDiag"] = torch.zeros((ldx,), dtype=f32, device=dev)
         s["lm"] = torch.zeros((ldx,), dtype=f32, device=dev)
@@ -590,6 +637,9 @@ class Morpho_pairwise:
         seg2 = self._choose_segments(nrb, nbb)
         seg_alloc = max(seg2, self._choose_segments(nrb, nbb_alloc))
         s["rowpart"] = torch.zeros((seg_alloc, 8, ldx), dtype=f32, device=dev)
+        s["bbox"] = torch.zeros((nrb, 8), dtype=f32, device=dev)
+        s["collist"] = torch.zeros((nrb, self._nbb_pad), dtype=torch.int32, device=dev)
+        s["colcount"] = torch.zeros((nrb,), dtype=torch.int32, device=dev)
         s["UtWU"] = torch.zeros((K, K), dtype=f64, device=dev)
         s["UtPXB"] = torch.zeros((K, 3), dtype=f64, device=dev)
         s["SigmaInv"] = torch.zeros((K, K), dtype=f64, device=dev)
@@ -625,6 +675,7 @@ class Morpho_pairwise:
         p.svi, p.nn_init, p.update_R = int(self.SVI_mode), int(self.nn_init), int(self.update_R)
         p.nonrigid_start_iter = int(self.nonrigid_start_iter)
         p.seg1, p.seg2, p.nbb_pad, p.trace = seg1, seg2, self._nbb_pad, 1
+        p.cull = int(bool(self.cull_zero_tiles))
         p.lambdaVF, p.gamma_a, p.gamma_b = float(self.lambdaVF), float(self.gamma_a), float(self.gamma_b)
         p.samples_s = float(self.samples_s)
         p.nn_init_weight = float(self.nn_init_weight)
@@ -648,7 +699,8 @@ class Morpho_pairwise:
         p.GT, p.UT = ptr(self._GT).value, ptr(self._UT).value
         for name in ("xa", "xb4", "Gamma", "kappa", "batch_idx", "alpha", "SigmaDiag", "lm", "mm", "VnA", "RnA", "XAHat",
                      "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart",
-                     "rowpart", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc", "trace_buf"):
+                     "rowpart", "bbox", "collist", "colcount", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc",
+                     "trace_buf"):
             t = s[name]
             setattr(p, name, None if t is None else t.data_ptr())
         p.jacobi_ws = None
@@ -705,6 +757,7 @@ class Morpho_pairwise:
         lib, p = self._lib, self._params
         check(lib.spb_iter_begin(C.byref(p), it, st), "spb_iter_begin")
         check(lib.spb_gather_cols(C.byref(p), it, st), "spb_gather_cols")
+        check(lib.spb_estep_col_lists(C.byref(p), st), "spb_estep_col_lists")
         if sweep_events is not None:
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
@@ -824,17 +877,20 @@ class Morpho_pairwise:
         self.Sp, self.Sp_spatial, self.Sp_sigma2 = sc.Sp, sc.Sp_spatial, sc.Sp_sigma2
         self.nonrigid_flag = self.max_iter - 1 > self.nonrigid_start_iter
 
-        def rows(name):  # [3, ldx] SoA -> [NA, D]
-            return s[name][:D, :NA].T.contiguous().cpu().numpy().astype(dt)
+        def rows(name):  # [3, ldx] SoA (processing order) -> [NA, D] in the caller's row order
+            return self._unsorted(s[name][:D, :NA].T.contiguous().cpu().numpy().astype(dt))
+
+        def vec(name):
+            return self._unsorted(s[name][:NA].cpu().numpy().astype(dt))
 
         self.XAHat, self.RnA, self.VnA = rows("XAHat"), rows("RnA"), rows("VnA")
         self.optimal_RnA = (self.coordsA.astype(np.float64) @ self.optimal_R.astype(np.float64).T + self.optimal_t).astype(dt)
-        self.K_NA = s["K_NA"][:NA].cpu().numpy().astype(dt)
+        self.K_NA = vec("K_NA")
         self.K_NB = s["K_NB"][: self._NBb].cpu().numpy().astype(dt)
-        self.K_NA_spatial = s["K_NA_spatial"][:NA].cpu().numpy().astype(dt)
-        self.K_NA_sigma2 = s["K_NA_sigma2"][:NA].cpu().numpy().astype(dt)
-        self.alpha = s["alpha"][:NA].cpu().numpy().astype(dt)
-        self.SigmaDiag = s["SigmaDiag"][:NA].cpu().numpy().astype(dt)
+        self.K_NA_spatial = vec("K_NA_spatial")
+        self.K_NA_sigma2 = vec("K_NA_sigma2")
+        self.alpha = vec("alpha")
+        self.SigmaDiag = vec("SigmaDiag")
         if self.nonrigid_flag:
             self.Coff = s["Coff"][:, :D].cpu().numpy().astype(dt)
             self.SigmaInv = s["SigmaInv"].cpu().numpy().astype(dt)
@@ -845,12 +901,16 @@ class Morpho_pairwise:
             if getattr(self, "_P_dev", None) is None:  # max_iter == 0 or the return_mapping E-step above
                 self._P_dev = torch.empty((NA, self._NBb), dtype=torch.float32, device=self._dev)
                 check(lib.spb_materialize_P(C.byref(p), last_iter, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
-            self.P = self._P_dev.cpu().numpy().astype(dt)
+            self.P = self._unsorted(self._P_dev.cpu().numpy().astype(dt))
             self._P_dev = None
         else:
             self.P = None
         if self.iter_key_added is not None:
             hist = s["hist"][:, :D, :NA].permute(0, 2, 1).contiguous().cpu().numpy().astype(dt)
+            if self._perm is not None:
+                un = np.empty_like(hist)
+                un[:, self._perm, :] = hist
+                hist = un
             sig = s["hist_sigma2"].cpu().numpy()
             self.iter_added = {self.key_added: {}, "sigma2": {}}
             for it in range(self.max_iter):

@@ -31,29 +31,46 @@ struct __align__(16) SmemLayoutT {
   uint64_t empty[kStages];
 };
 
-// One stage = kColStage GT rows (4 KB each) + the columns' constants. Segments are multiples of kColStage columns, so
-// only the final stage of the whole matrix can be ragged: its missing columns re-read the last valid GT row and take
-// all-zero constants (the constant arrays are zero-padded), which keeps the consumer loops branch-free.
+// Column work lists. Every row block owns a compacted list of the columns of this iteration that can interact with it
+// (build_col_lists_kernel): with culling on, a column whose squared distance to the block's bounding box makes
+// exp(-d / 2 sigma2) flush to zero in fp32 contributes EXACTLY nothing to any sum and is dropped — bit-identical results,
+// less HBM traffic. A CTA (rb, seg) takes a contiguous slice of its block's list.
+struct ColRange {
+  int begin, end;
+};
+template <int kColStage>
+__device__ __forceinline__ ColRange col_range(const int32_t* __restrict__ colcount, int rb, int seg, int nseg) {
+  const int count = colcount[rb];
+  int cps = (count + nseg - 1) / nseg;
+  cps = ((cps + kColStage - 1) / kColStage) * kColStage;
+  ColRange r;
+  r.begin = min(count, seg * cps);
+  r.end = min(count, r.begin + cps);
+  return r;
+}
+
+// One stage = kColStage GT rows (4 KB each) + the columns' constants. Slots past the end of the slice re-read a valid GT
+// row and take the all-zero constant entry at index NBb (the constant arrays are zero-padded), which keeps the consumer
+// loops branch-free.
 template <int kColStage, int kStages>
 __device__ __forceinline__ void producer_loop(SmemLayoutT<kColStage, kStages>& sm, const float* __restrict__ GT, int64_t ldx,
-                                              const int32_t* __restrict__ col_index, const float* __restrict__ colsrc,
-                                              int col_floats, int i0, int j_begin, int j_end, int NBb, int lane) {
-  const int nst = (j_end - j_begin + kColStage - 1) / kColStage;
+                                              const int32_t* __restrict__ col_index, const int32_t* __restrict__ list,
+                                              const float* __restrict__ colsrc, int col_floats, int i0, ColRange cr,
+                                              int NBb, int lane) {
+  const int nst = (cr.end - cr.begin + kColStage - 1) / kColStage;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     if (st >= kStages) mbar_wait(&sm.empty[s], ((st / kStages) - 1) & 1);
-    const int jb = j_begin + st * kColStage;
+    const int pb = cr.begin + st * kColStage;
     if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)(kColStage * kRowTile * 4 + kColStage * col_floats * 4));
     __syncwarp();
     if (lane < kColStage) {
-      const int j = min(jb + lane, NBb - 1);
-      const int64_t row = col_index ? (int64_t)col_index[j] : (int64_t)j;
+      const bool live = pb + lane < cr.end;
+      const int j = live ? list[pb + lane] : NBb;          // NBb = zero-constant pad entry
+      const int jr = live ? j : list[cr.end - 1];          // any valid GT row for pad slots
+      const int64_t row = col_index ? (int64_t)col_index[jr] : (int64_t)jr;
       bulk_g2s(&sm.tile[s][lane][0], GT + row * ldx + i0, kRowTile * 4, &sm.full[s]);
-      if (col_floats == 16) {
-        if (lane == 0) bulk_g2s(&sm.cols[s][0][0], colsrc + (int64_t)jb * 16, kColStage * 64, &sm.full[s]);
-      } else {
-        bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)(jb + lane) * 8, 32, &sm.full[s]);
-      }
+      bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)j * col_floats, col_floats * 4, &sm.full[s]);
     }
   }
 }
@@ -140,16 +157,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colgeom, const float* __restrict__ XA, const float* __restrict__ lm,
                     const float* __restrict__ mm, const spb_scalars* __restrict__ sc, float* __restrict__ colpart,
-                    int NBb, int nbb_pad, int cols_per_seg) {
+                    int NBb, int nbb_pad, const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using Smem = SmemLayoutT<kColStage, kStages>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
-  const int j_begin = seg * cols_per_seg;
-  const int j_end = min(NBb, j_begin + cols_per_seg);
-  if (j_begin >= j_end) return;
+  const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
+  const int32_t* list = collist + (int64_t)rb * nbb_pad;
+  if (cr.begin >= cr.end) return;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -160,7 +177,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   __syncthreads();
 
   if (warp == kConsumers / 32) {
-    producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, colgeom, 8, i0, j_begin, j_end, NBb, lane);
+    producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, list, colgeom, 8, i0, cr, NBb, lane);
     return;
   }
   // ---- consumers: 4 rows per thread = 2 packed row pairs ----
@@ -174,11 +191,11 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const u64 xa0 = pk(X0.x, X0.y), xb0 = pk(X0.z, X0.w), xa1 = pk(X1.x, X1.y), xb1 = pk(X1.z, X1.w);
   const u64 xa2 = pk(X2.x, X2.y), xb2 = pk(X2.z, X2.w);
   const u64 lma = pk(LM.x, LM.y), lmb = pk(LM.z, LM.w), mma = pk(MM.x, MM.y), mmb = pk(MM.z, MM.w);
-  const int nst = (j_end - j_begin + kColStage - 1) / kColStage;
+  const int nst = (cr.end - cr.begin + kColStage - 1) / kColStage;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     mbar_wait(&sm.full[s], (st / kStages) & 1);
-    const int jb = j_begin + st * kColStage;
+    const int pb = cr.begin + st * kColStage;
     constexpr int NV = 4 * kColStage;  // partial sums per thread per stage, index v * kColStage + jj
     float acc[NV];
 #pragma unroll
@@ -207,7 +224,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
 #pragma unroll
       for (int w = 0; w < kConsumers / 32; ++w) t += sm.red[buf][w][lane];
       const int v = lane / kColStage, jj = lane % kColStage;
-      if (jb + jj < j_end) colpart[((int64_t)rb * 4 + v) * nbb_pad + jb + jj] = t;
+      if (pb + jj < cr.end) colpart[((int64_t)rb * 4 + v) * nbb_pad + list[pb + jj]] = t;
     }
   }
 }
@@ -248,15 +265,17 @@ template <int kColStage, int kStages, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
-                    const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int cols_per_seg) {
+                    const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int nbb_pad,
+                    const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using Smem = SmemLayoutT<kColStage, kStages>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
-  const int j_begin = seg * cols_per_seg;
-  const int j_end = min(NBb, j_begin + cols_per_seg);
+  const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
+  const int32_t* list = collist + (int64_t)rb * nbb_pad;
+  const int j_begin = cr.begin, j_end = cr.end;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sm.full[s], 1);
@@ -266,7 +285,7 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   }
   __syncthreads();
   if (warp == kConsumers / 32) {
-    if (j_begin < j_end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, colconst, 16, i0, j_begin, j_end, NBb, lane);
+    if (j_begin < j_end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, list, colconst, 16, i0, cr, NBb, lane);
     return;
   }
   const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
@@ -356,6 +375,101 @@ __global__ void row_finalize_kernel(const float* __restrict__ rowpart, int nseg,
   block_reduce_atomic<4>(v, sc->sums);
 }
 
+// bounding box of the current positions of each row block (valid rows only)
+__global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restrict__ XA, int ldx, int NA,
+                                                           float* __restrict__ bbox) {
+  __shared__ float red[6][8];
+  const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+  for (int q = 0; q < 4; ++q) {
+    const int i = rb * kRowTile + threadIdx.x * 4 + q;
+    if (i < NA) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const float x = XA[(int64_t)d * ldx + i];
+        lo[d] = fminf(lo[d], x);
+        hi[d] = fmaxf(hi[d], x);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    if (lane == 0) {
+      red[d][warp] = lo[d];
+      red[3 + d][warp] = hi[d];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = red[threadIdx.x][0];
+    for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+    bbox[rb * 8 + threadIdx.x] = v;
+  }
+}
+
+// Per row block: order-preserving compaction of the columns that are not provably zero for every row of the block.
+// A column j is dropped when c_q * dmin^2 < -127 (log2 domain, with a 1e-5 relative safety margin), dmin = distance from
+// y_j to the block's bounding box: then ex2(c_q d + lm) and ex2(c_s d) flush to +0 for every pair of the block (lm <= 0,
+// c_s <= c_q < 0), so the dropped pairs would have added exact zeros.
+__global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
+                                                               int NBb, spb_scalars* __restrict__ sc, int cull,
+                                                               int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
+                                                               int nbb_pad) {
+  __shared__ int warp_cnt[32];
+  __shared__ int base;
+  const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float cq = sc->c_q * (1.0f - 1e-5f);
+  float lo[3], hi[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    lo[d] = bbox[rb * 8 + d];
+    hi[d] = bbox[rb * 8 + 3 + d];
+  }
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  int32_t* list = collist + (int64_t)rb * nbb_pad;
+  for (int j0 = 0; j0 < NBb; j0 += 1024) {
+    const int j = j0 + threadIdx.x;
+    bool keep = false;
+    if (j < NBb) {
+      keep = true;
+      if (cull) {
+        const float* y = colgeom + (int64_t)j * 8;
+        float d2 = 0.f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float yd = y[2 * d];
+          const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
+          d2 = fmaf(g, g, d2);
+        }
+        keep = cq * d2 >= -127.0f;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (keep) list[off + __popc(m & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int t = 0;
+      for (int w = 0; w < 32; ++w) t += warp_cnt[w];
+      base += t;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    colcount[rb] = base;
+    atomicAdd(&sc->visited, (double)base);
+  }
+}
+
 // gather this iteration's fixed-slice coordinates (SVI batch or all columns) (morpho_class.py:1149)
 __global__ void gather_cols_kernel(const float* __restrict__ xb4, const int32_t* __restrict__ idx, int NBb,
                                    float* __restrict__ colgeom) {
@@ -398,14 +512,6 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
 
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
-int cfg_cols() { return g_sweep_cfg == 0 ? 8 : 4; }
-
-int cols_per_segment(int NBb, int nseg) {
-  const int cs = cfg_cols();
-  int c = (NBb + nseg - 1) / nseg;
-  return ((c + cs - 1) / cs) * cs;
-}
-
 template <int C, int S, int B>
 int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
@@ -417,7 +523,7 @@ int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   }
   dim3 grid(p->ldx / kRowTile, p->seg1);
   estep_sweep1_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
-                                                                  p->colpart, p->NBb, p->nbb_pad, cols_per_segment(p->NBb, p->seg1));
+                                                                  p->colpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
 
@@ -432,7 +538,7 @@ int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   }
   dim3 grid(p->ldx / kRowTile, p->seg2);
   estep_sweep2_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
-                                                                  p->rowpart, p->NBb, cols_per_segment(p->NBb, p->seg2));
+                                                                  p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
 
@@ -454,8 +560,22 @@ extern "C" int spb_set_sweep_config(int32_t cfg) {
   return 0;
 }
 
+extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
+  const int nrb = p->ldx / kRowTile;
+  block_bounds_kernel<<<nrb, 256, 0, (cudaStream_t)stream>>>(p->XAHat, p->ldx, p->NA, p->bbox);
+  SPB_CHECK_LAUNCH();
+  build_col_lists_kernel<<<nrb, 1024, 0, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
+                                                                 p->colcount, p->nbb_pad);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
+  {  // partial column sums of (row block, column) combinations that are not visited must read as zero
+    cudaError_t e = cudaMemsetAsync(p->colpart, 0, sizeof(float) * (size_t)(p->ldx / kRowTile) * 4 * p->nbb_pad, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   if (g_sweep_cfg == 1) rc = launch_sweep1<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep1<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep1<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);

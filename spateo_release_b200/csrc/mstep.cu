@@ -21,6 +21,7 @@ __global__ void iter_begin_kernel(spb_em_params p, int iter) {
     sc->step = p.svi ? fmin(1.0, 10.0 / (iter + 1.0)) : 1.0;  // morpho_class.py:894
     for (int q = 0; q < 8; ++q) sc->sums[q] = 0.0;
     sc->dotKS = 0.0;
+    sc->visited = 0.0;
     const double s2 = sc->sigma2, g = sc->gamma;
     const double outlier_s = p.samples_s * (double)p.NA;                                   // utils.py:1051
     sc->omega = pow(kTwoPi * s2, 0.5 * p.D) * (1.0 - g) / (g * outlier_s);                 // utils.py:1053
@@ -475,7 +476,7 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
   if (p.trace && p.trace_buf) {
     double* tr = p.trace_buf + (int64_t)iter * SPB_TRACE_STRIDE;
     tr[0] = sc->sigma2; tr[1] = sc->gamma; tr[2] = sc->Sp; tr[3] = sc->Sp_spatial;
-    tr[4] = sc->Sp_sigma2; tr[5] = sc->sigma2_variance; tr[6] = sc->sigma2_related; tr[7] = sc->step;
+    tr[4] = sc->Sp_sigma2; tr[5] = sc->sigma2_variance; tr[6] = sc->sigma2_related; tr[7] = sc->visited;
   }
 }
 
@@ -655,6 +656,7 @@ extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stre
   if (nonrigid && p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
   SPB_TRY(spb_iter_begin(p, iter, stream));
   SPB_TRY(spb_gather_cols(p, iter, stream));
+  SPB_TRY(spb_estep_col_lists(p, stream));
   SPB_TRY(spb_estep_sweep1(p, iter, stream));
   SPB_TRY(spb_col_finalize(p, stream));
   SPB_TRY(spb_estep_sweep2(p, iter, stream));

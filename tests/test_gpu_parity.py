@@ -121,6 +121,7 @@ def _poke_estep_state(m, g, it, sfx=""):
     alpha = g[f"it{it}_in_alpha{sfx}"].astype(np.float64)
     SigmaDiag = g[f"it{it}_in_SigmaDiag{sfx}"].astype(np.float64)
     sigma2 = float(g[f"it{it}_in_sigma2{sfx}"])
+    XAHat, alpha, SigmaDiag = m._sorted(XAHat), m._sorted(alpha), m._sorted(SigmaDiag)  # device rows are in processing order
     s["XAHat"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(XAHat.T)).to(dev)
     s["alpha"][:NA] = torch.from_numpy(alpha.astype(np.float32)).to(dev)
     s["SigmaDiag"][:NA] = torch.from_numpy(SigmaDiag.astype(np.float32)).to(dev)
@@ -154,7 +155,8 @@ def test_single_estep_matches_float64_oracle(golden, case, it):
     from spateo_release_b200._capi import check, ptr
 
     check(m._lib.spb_materialize_P(C.byref(m._params), it, ptr(Pd), NB, C.c_void_p(st)), "materialize")
-    P = Pd.cpu().numpy()
+    P = m._unsorted(Pd.cpu().numpy())
+    dvec = lambda name: m._unsorted(m._state[name][:NA].cpu().numpy())
     # float64 oracle on the same (fp32-valued) inputs
     f8 = lambda k: g[k].astype(np.float64)
     XAHat, alpha, SD = f8(f"it{it}_in_XAHat"), f8(f"it{it}_in_alpha"), f8(f"it{it}_in_SigmaDiag")
@@ -172,11 +174,11 @@ def test_single_estep_matches_float64_oracle(golden, case, it):
           f"max-abs ours {np.abs(P - P64).max():.2e} (Pmax {P64.max():.2e})")
     assert _relF(P, P64) < 1e-4
     assert np.abs(P - P64).max() < 1e-4 * P64.max()
-    assert _relmax(m._state["K_NA"][:NA].cpu().numpy(), P64.sum(1)) < 1e-4
+    assert _relmax(dvec("K_NA"), P64.sum(1)) < 1e-4
     assert _relmax(m._state["K_NB"][:NB].cpu().numpy(), P64.sum(0)) < 1e-4
-    assert _relmax(m._state["K_NA_spatial"][:NA].cpu().numpy(), kns) < 1e-4
-    assert _relmax(m._state["K_NA_sigma2"][:NA].cpu().numpy(), kn2) < 1e-4
-    pxb = m._state["PXB"][: m.D, :NA].T.cpu().numpy()
+    assert _relmax(dvec("K_NA_spatial"), kns) < 1e-4
+    assert _relmax(dvec("K_NA_sigma2"), kn2) < 1e-4
+    pxb = m._unsorted(m._state["PXB"][: m.D, :NA].T.contiguous().cpu().numpy())
     assert _relmax(pxb, P64 @ yb) < 1e-4
     sc = m._read_scalars()
     assert abs(sc.sums[3] - s2r) < 1e-4 * abs(s2r)
@@ -340,3 +342,48 @@ def test_large_pair_invariants():
     assert np.isfinite(m.XAHat).all() and float(m.sigma2) >= 1e-3
     # the recovered rigid motion maps B back onto A: residual small compared with the slice extent
     assert m.trace[-1, 0] < m.trace[0, 0]
+
+
+def test_zero_tile_culling_is_exact():
+    """Morton-ordered row blocks + culling of tiles whose pairs all underflow to 0: same results as the dense sweep up
+    to fp32 summation order, and a large share of the tiles is really skipped once sigma2 is small."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(6000, 5000, 40, dim=2, seed=11)
+    outs = []
+    for cull in (False, True):
+        np.random.seed(0)
+        m = st.align.Morpho_pairwise(B, A, device="0", verbose=False, SVI_mode=False, max_iter=140, nn_init=False,
+                                     cull_zero_tiles=cull, spatial_sort=True)
+        P = m.run()
+        cnt = m._state["colcount"].cpu().numpy()
+        outs.append((m, P, cnt))
+    (m0, P0, c0), (m1, P1, c1) = outs
+    assert np.all(c0 == m0.NB), "dense mode must visit every column"
+    assert c1.sum() < 0.8 * c0.sum(), f"expected substantial culling at sigma2={float(m1.sigma2):.4g}: {c1.sum()} of {c0.sum()}"
+    scale = np.abs(m0.XAHat).max()
+    assert np.abs(m0.XAHat - m1.XAHat).max() < 2e-6 * scale
+    assert np.abs(m0.optimal_RnA - m1.optimal_RnA).max() < 2e-6 * scale
+    assert np.abs(m0.K_NA - m1.K_NA).max() < 1e-5 * np.abs(m0.K_NA).max()
+    assert np.array_equal(P0 == 0, P1 == 0) or np.abs(P0 - P1).max() < 1e-6
+    assert abs(float(m0.sigma2) - float(m1.sigma2)) < 1e-6 * float(m0.sigma2)
+
+
+def test_spatial_sort_off_matches_on():
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(3000, 2500, 30, dim=3, seed=12, z_thickness=15.0)
+    res = []
+    for srt in (False, True):
+        np.random.seed(0)
+        m = st.align.Morpho_pairwise(B, A, device="0", verbose=False, SVI_mode=True, max_iter=100, spatial_sort=srt,
+                                     cull_zero_tiles=srt, vecfld_key_added="vf")
+        P = m.run()
+        res.append((m, P))
+    (a, Pa), (b, Pb) = res
+    scale = np.abs(a.XAHat).max()
+    assert np.abs(a.XAHat - b.XAHat).max() < 5e-6 * scale
+    assert np.abs(Pa - Pb).max() < 1e-5
+    assert np.abs(a.U - b.U).max() < 1e-7
