@@ -144,9 +144,10 @@ int spb_sizeof_em_params(void);
 int spb_sizeof_scalars(void);
 
 /* ---- expression cost matrix: calc_distance + calc_probability (utils.py:647-788, :866-985) ------------------- */
-/* KL pre-pass: Xn=(X+.01)/rowsum, xlogx=sum Xn log(Xn+1e-8); with is_fixed!=0 writes log(Xn+1e-8) instead. */
+/* KL pre-pass: Xn=(X+.01)/rowsum, xlogx=sum Xn log(Xn+1e-8); with is_fixed!=0 writes log(Xn+1e-8) instead, optionally
+   centred by c_j = sum_g center_w[g] * (that row) which is returned in rowterm (the cost epilogue adds it back). */
 int spb_kl_prepare_rows(const float* X, int64_t n, int64_t G, int64_t ldin, float* out, int64_t ldout, float* rowterm,
-                        int32_t is_fixed, void* stream); /* utils.py:683-695 */
+                        int32_t is_fixed, const float* center_w, void* stream); /* utils.py:683-695 */
 /* row squared norms (euc) or row-normalisation (cos) */
 int spb_rows_sqnorm(const float* X, int64_t n, int64_t G, int64_t ldin, float* rowterm, void* stream); /* utils.py:780 */
 int spb_rows_normalize(const float* X, int64_t n, int64_t G, int64_t ldin, float* out, int64_t ldout, void* stream); /* utils.py:736-739 */
@@ -154,6 +155,12 @@ int spb_rows_normalize(const float* X, int64_t n, int64_t G, int64_t ldin, float
 int spb_gene_cost(const float* A, int64_t lda, const float* rowtermA, const float* B, int64_t ldb, const float* rowtermB,
                   int64_t NA, int64_t NB, int64_t G, int32_t metric, int32_t prob_type, float prob_param,
                   int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:697,780-783,742 + :977-981 */
+/* tensor-core variant (tcgen05.mma kind::tf32, 3xTF32 split: operands given as hi/lo pairs, zero-padded to 32 features) */
+int spb_split_tf32(const float* x, float* hi, float* lo, int64_t n, void* stream);
+int spb_gene_cost_tc(const float* A_hi, const float* A_lo, int64_t lda, const float* rowtermA, const float* B_hi,
+                     const float* B_lo, int64_t ldb, const float* rowtermB, int64_t NA, int64_t NB, int64_t G, int32_t metric,
+                     int32_t prob_type, float prob_param, int32_t accumulate, float* GT, int64_t ldx,
+                     void* stream); /* utils.py:697,780-783,742 + :977-981 */
 /* label layer: GT[j][i] (op)= LT[labA_i][labB_j] */
 int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, int32_t nB_labels, int64_t NA, int64_t NB,
                    int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:830 */

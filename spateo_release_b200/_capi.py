@@ -107,10 +107,12 @@ def load_library():
         "spb_launch_count": ([], C.c_int64),
         "spb_sizeof_em_params": ([], C.c_int),
         "spb_sizeof_scalars": ([], C.c_int),
-        "spb_kl_prepare_rows": ([P, I64, I64, I64, P, I64, P, I32, P], C.c_int),
+        "spb_kl_prepare_rows": ([P, I64, I64, I64, P, I64, P, I32, P, P], C.c_int),
         "spb_rows_sqnorm": ([P, I64, I64, I64, P, P], C.c_int),
         "spb_rows_normalize": ([P, I64, I64, I64, P, I64, P], C.c_int),
         "spb_gene_cost": ([P, I64, P, P, I64, P, I64, I64, I64, I32, I32, F, I32, P, I64, P], C.c_int),
+        "spb_split_tf32": ([P, P, P, I64, P], C.c_int),
+        "spb_gene_cost_tc": ([P, P, I64, P, P, P, I64, P, I64, I64, I64, I32, I32, F, I32, P, I64, P], C.c_int),
         "spb_label_cost": ([P, P, P, I32, I64, I64, I32, P, I64, P], C.c_int),
         "spb_set_sweep_config": ([I32], C.c_int),
         "spb_gather_cols": ([EP, I32, P], C.c_int),

@@ -74,21 +74,32 @@ def resolve_device(device) -> torch.device:
 
 
 class GeneCostBuilder:
-    """Device pipeline for ``calc_distance`` + ``calc_probability`` of one representation layer (utils.py:866-985)."""
+    """Device pipeline for ``calc_distance`` + ``calc_probability`` of one representation layer (utils.py:866-985).
 
-    def __init__(self, lib, dev):
+    Two contraction back-ends behind the same call: ``tensor`` (default) = tcgen05 / TMEM / TMA kernel with a 3xTF32
+    error-compensated split (fp32-accurate), ``simt`` = packed-FFMA2 register-tiled kernel with two-level accumulation.
+    """
+
+    def __init__(self, lib, dev, backend: Optional[str] = None):
+        import os
+
         self.lib, self.dev = lib, dev
+        self.backend = backend or os.environ.get("SPB_GENE_COST", "tensor")
 
-    def prepare(self, X: torch.Tensor, metric: str, fixed: bool):
-        """Row pre-pass. Returns (operand [n, Gp] fp32 zero-padded to 16 features, rowterm [n] or None)."""
+    def prepare(self, X: torch.Tensor, metric: str, fixed: bool, centre: Optional[torch.Tensor] = None):
+        """Row pre-pass. Returns (operand [n, Gp] fp32 zero-padded to 32 features, rowterm [n] or None).
+
+        KL, fixed side: ``centre`` (the mean normalised moving profile, length G) centres every log-row so the contraction
+        stays near zero (see kl_prepare_rows_kernel); the centring term comes back as the row term."""
         n, G = X.shape
-        Gp = _round_up(G, 16)
+        Gp = _round_up(G, 32)
         st = _capi.current_stream_ptr()
         if metric == "kl":
             out = torch.empty((n, Gp), dtype=torch.float32, device=self.dev)
-            rt = None if fixed else torch.empty((n,), dtype=torch.float32, device=self.dev)
-            check(self.lib.spb_kl_prepare_rows(ptr(X), n, G, X.stride(0), ptr(out), Gp, ptr(rt), 1 if fixed else 0, st),
-                  "spb_kl_prepare_rows")
+            want_rt = (not fixed) or (centre is not None)
+            rt = torch.empty((n,), dtype=torch.float32, device=self.dev) if want_rt else None
+            check(self.lib.spb_kl_prepare_rows(ptr(X), n, G, X.stride(0), ptr(out), Gp, ptr(rt), 1 if fixed else 0,
+                                               ptr(centre), st), "spb_kl_prepare_rows")
             return out, rt
         if metric in ("cos", "cosine"):
             out = torch.empty((n, Gp), dtype=torch.float32, device=self.dev)
@@ -104,12 +115,36 @@ class GeneCostBuilder:
         check(self.lib.spb_rows_sqnorm(ptr(out), n, G, Gp, ptr(rt), st), "spb_rows_sqnorm")
         return out, rt
 
-    def cost(self, opA, rtA, opB, rtB, NA, NB, G, metric, prob_type, prob_param, accumulate, GT, ldx):
+    @staticmethod
+    def centre_of(opA: torch.Tensor, G: int) -> torch.Tensor:
+        """Mean normalised moving profile (fp32, length G) used to centre the fixed side of the KL contraction."""
+        return opA[:, :G].mean(dim=0, dtype=torch.float64).float().contiguous()
+
+    def _split(self, op: torch.Tensor):
+        hi, lo = torch.empty_like(op), torch.empty_like(op)
+        check(self.lib.spb_split_tf32(ptr(op), ptr(hi), ptr(lo), op.numel(), _capi.current_stream_ptr()), "spb_split_tf32")
+        return hi, lo
+
+    def cost(self, opA, rtA, opB, rtB, NA, NB, G, metric, prob_type, prob_param, accumulate, GT, ldx, backend=None):
+        backend = backend or self.backend
+        pp = float(prob_param) if prob_param is not None else 1.0
+        if backend == "tensor":
+            ahi, alo = self._split(opA)
+            bhi, blo = self._split(opB)
+            check(
+                self.lib.spb_gene_cost_tc(
+                    ptr(ahi), ptr(alo), opA.stride(0), ptr(rtA), ptr(bhi), ptr(blo), opB.stride(0), ptr(rtB), NA, NB, G,
+                    _METRIC_CODE[metric], _PROB_CODE[prob_type], pp, 1 if accumulate else 0, ptr(GT), ldx,
+                    _capi.current_stream_ptr(),
+                ),
+                "spb_gene_cost_tc",
+            )
+            self._keep = (ahi, alo, bhi, blo)  # stay alive until the stream has consumed them
+            return
         check(
             self.lib.spb_gene_cost(
                 ptr(opA), opA.stride(0), ptr(rtA), ptr(opB), opB.stride(0), ptr(rtB), NA, NB, G, _METRIC_CODE[metric],
-                _PROB_CODE[prob_type], float(prob_param) if prob_param is not None else 1.0, 1 if accumulate else 0,
-                ptr(GT), ldx, _capi.current_stream_ptr(),
+                _PROB_CODE[prob_type], pp, 1 if accumulate else 0, ptr(GT), ldx, _capi.current_stream_ptr(),
             ),
             "spb_gene_cost",
         )
@@ -392,9 +427,9 @@ class Morpho_pairwise:
         A = torch.from_numpy(np.ascontiguousarray(XA_host, dtype=np.float32)).to(dev)
         B = torch.from_numpy(np.ascontiguousarray(XB_host, dtype=np.float32)).to(dev)
         opA, rtA = gc.prepare(A, metric, fixed=False)
-        opB, rtB = gc.prepare(B, metric, fixed=True)
+        opB, rtB = gc.prepare(B, metric, fixed=True, centre=gc.centre_of(opA, A.shape[1]) if metric == "kl" else None)
         nA, nB, G = A.shape[0], B.shape[0], A.shape[1]
-        lds = _round_up(nA, 128)
+        lds = _round_up(nA, 256)
         ET = torch.empty((nB, lds), dtype=torch.float32, device=dev)
         gc.cost(opA, rtA, opB, rtB, nA, nB, G, metric, "prob", None, False, ET, lds)
         return ET, nA
@@ -561,7 +596,7 @@ class Morpho_pairwise:
                     A = A.index_select(0, self._perm_dev)  # moving cells in Morton order
                 B = self._to_device_pinned(eB)
                 opA, rtA = gc.prepare(A, d_s, fixed=False)
-                opB, rtB = gc.prepare(B, d_s, fixed=True)
+                opB, rtB = gc.prepare(B, d_s, fixed=True, centre=gc.centre_of(opA, eA.shape[1]) if d_s == "kl" else None)
                 gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, eA.shape[1], d_s, p_t, p_p, not first, self._GT, self.ldx)
                 del A, B, opA, opB
             first = False

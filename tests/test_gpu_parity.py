@@ -69,7 +69,7 @@ def test_gene_cost_kl_matches_oracle(golden):
     B = torch.from_numpy(g["exp_fixed"]).to(dev)
     gc = GeneCostBuilder(lib, dev)
     opA, rtA = gc.prepare(A, "kl", fixed=False)
-    opB, rtB = gc.prepare(B, "kl", fixed=True)
+    opB, rtB = gc.prepare(B, "kl", fixed=True, centre=gc.centre_of(opA, A.shape[1]))
     NA, NB, G = A.shape[0], B.shape[0], A.shape[1]
     ldx = 1024
     GT = torch.full((NB, ldx), -1.0, dtype=torch.float32, device=dev)
