@@ -239,18 +239,33 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
   __syncthreads();
   const int npair = Kp / 2;
   for (int sweep = 0; sweep < 30; ++sweep) {
-    if (tid == 0) {
+    // convergence: off-diagonal mass below 1e-30 of the diagonal mass (eigenvalues then carry ~1e-15 relative error)
+    {
       double off = 0, dg = 0;
-      for (int r = 0; r < Kp; ++r)
-        for (int c = 0; c < Kp; ++c) {
-          const double a = A[r * Kp + c];
-          if (r == c) dg += a * a; else off += a * a;
+      for (int q = tid; q < Kp * Kp; q += nt) {
+        const double a = A[q];
+        if (q / Kp == q % Kp) dg += a * a; else off += a * a;
+      }
+      off = warp_sum(off);
+      dg = warp_sum(dg);
+      __shared__ double r_off[8], r_dg[8];
+      if ((tid & 31) == 0) {
+        r_off[tid >> 5] = off;
+        r_dg[tid >> 5] = dg;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double o = 0, d = 0;
+        for (int w = 0; w < (nt >> 5); ++w) {
+          o += r_off[w];
+          d += r_dg[w];
         }
-      s_off = off;
-      s_diag = dg;
+        s_off = o;
+        s_diag = d;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    if (s_off <= 1e-40 * s_diag || s_off == 0.0) break;
+    if (s_off <= 1e-30 * s_diag || s_off == 0.0) break;
     for (int stp = 0; stp < Kp - 1; ++stp) {
       if (tid < npair) {
         const int pp = min(top[tid], bot[tid]), qq = max(top[tid], bot[tid]);
