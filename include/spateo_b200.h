@@ -41,6 +41,7 @@ extern "C" {
 #define SPB_METRIC_EUC 1 /* "euc"/"euclidean": SQUARED distance (reference quirk) */
 #define SPB_METRIC_COS 2
 #define SPB_METRIC_SQRT_EUC 3 /* "square_euc": sqrt of the squared distance (reference quirk) */
+#define SPB_METRIC_SYMKL 4    /* "sym_kl": operands are [Xn | log X] and [log Y | Yn]; e = (rowA + rowB - dot) / 2 */
 #define SPB_PROB_GAUSS 0
 #define SPB_PROB_COS 1
 #define SPB_PROB_PROB 2

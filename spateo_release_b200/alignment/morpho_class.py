@@ -28,6 +28,7 @@ _METRIC_CODE = {
     "square_euclidean": _capi.CONST["SPB_METRIC_SQRT_EUC"],
     "cos": _capi.CONST["SPB_METRIC_COS"],
     "cosine": _capi.CONST["SPB_METRIC_COS"],
+    "sym_kl": _capi.CONST["SPB_METRIC_SYMKL"],
 }
 _PROB_CODE = {
     "gauss": _capi.CONST["SPB_PROB_GAUSS"],
@@ -115,6 +116,26 @@ class GeneCostBuilder:
         check(self.lib.spb_rows_sqnorm(ptr(out), n, G, Gp, ptr(rt), st), "spb_rows_sqnorm")
         return out, rt
 
+    def prepare_pair(self, A: torch.Tensor, B: torch.Tensor, metric: str):
+        """Operands + row terms of (moving A, fixed B) for ``metric``. Returns (opA, rtA, opB, rtB, G_effective).
+
+        ``sym_kl`` = (KL(a||b) + KL(b||a)) / 2 (utils.py:922-932) is ONE contraction over 2G features:
+        [Xn | log X - d_i] . [log Y - c_j | Yn], with both log blocks centred (c_j by the mean moving profile, d_i by the
+        mean fixed profile) and e = ((sum Xn log X - d_i) + (sum Yn log Y - c_j) - dot) / 2."""
+        G = A.shape[1]
+        if metric != "sym_kl":
+            opA, rtA = self.prepare(A, metric, fixed=False)
+            opB, rtB = self.prepare(B, metric, fixed=True, centre=self.centre_of(opA, G) if metric == "kl" else None)
+            return opA, rtA, opB, rtB, G
+        Xn, ta = self.prepare(A, "kl", fixed=False)              # Xn, sum Xn (log Xn + log G)
+        Yn, tb = self.prepare(B, "kl", fixed=False)
+        LY, cj = self.prepare(B, "kl", fixed=True, centre=self.centre_of(Xn, G))   # log Y + log G - c_j
+        LX, di = self.prepare(A, "kl", fixed=True, centre=self.centre_of(Yn, G))   # log X + log G - d_i
+        Gp = Xn.shape[1]
+        opA = torch.cat([Xn, LX], dim=1).contiguous()
+        opB = torch.cat([LY, Yn], dim=1).contiguous()
+        return opA, (ta - di).contiguous(), opB, (tb - cj).contiguous(), 2 * Gp
+
     @staticmethod
     def centre_of(opA: torch.Tensor, G: int) -> torch.Tensor:
         """Mean normalised moving profile (fp32, length G) used to centre the fixed side of the KL contraction."""
@@ -160,7 +181,7 @@ class Morpho_pairwise:
     results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
     Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
     ``pre_compute_dist``. Not implemented in this round (raise NotImplementedError): ``sparse_calculation_mode``,
-    guidance pairs, ``kernel_type="geodist"``, ``dissimilarity="sym_kl"``.
+    guidance pairs, ``kernel_type="geodist"``.
     """
 
     def __init__(
@@ -334,8 +355,6 @@ class Morpho_pairwise:
             if self.kernel_type == "geodist":
                 raise NotImplementedError("kernel_type='geodist' is not implemented in spateo_release_b200 yet.")
             raise NotImplementedError(f"Kernel type '{self.kernel_type}' is not implemented.")
-        if "sym_kl" in self.dissimilarity:
-            raise NotImplementedError("dissimilarity='sym_kl' is not implemented in spateo_release_b200 yet.")
 
     # ------------------------------------------------------------------------------------------------------------------
     # preprocessing (morpho_class.py:443-558)
@@ -426,9 +445,8 @@ class Morpho_pairwise:
         gc = GeneCostBuilder(self._lib, dev)
         A = torch.from_numpy(np.ascontiguousarray(XA_host, dtype=np.float32)).to(dev)
         B = torch.from_numpy(np.ascontiguousarray(XB_host, dtype=np.float32)).to(dev)
-        opA, rtA = gc.prepare(A, metric, fixed=False)
-        opB, rtB = gc.prepare(B, metric, fixed=True, centre=gc.centre_of(opA, A.shape[1]) if metric == "kl" else None)
-        nA, nB, G = A.shape[0], B.shape[0], A.shape[1]
+        opA, rtA, opB, rtB, G = gc.prepare_pair(A, B, metric)
+        nA, nB = A.shape[0], B.shape[0]
         lds = _round_up(nA, 256)
         ET = torch.empty((nB, lds), dtype=torch.float32, device=dev)
         gc.cost(opA, rtA, opB, rtB, nA, nB, G, metric, "prob", None, False, ET, lds)
@@ -595,9 +613,8 @@ class Morpho_pairwise:
                 if self._perm is not None:
                     A = A.index_select(0, self._perm_dev)  # moving cells in Morton order
                 B = self._to_device_pinned(eB)
-                opA, rtA = gc.prepare(A, d_s, fixed=False)
-                opB, rtB = gc.prepare(B, d_s, fixed=True, centre=gc.centre_of(opA, eA.shape[1]) if d_s == "kl" else None)
-                gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, eA.shape[1], d_s, p_t, p_p, not first, self._GT, self.ldx)
+                opA, rtA, opB, rtB, G_eff = gc.prepare_pair(A, B, d_s)
+                gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, G_eff, d_s, p_t, p_p, not first, self._GT, self.ldx)
                 del A, B, opA, opB
             first = False
 

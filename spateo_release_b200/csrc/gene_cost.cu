@@ -116,6 +116,7 @@ __global__ void rows_normalize_kernel(const float* __restrict__ X, int64_t G, in
 __device__ __forceinline__ float cost_to_prob(float dot, float ta, float tb, int metric, int prob_type, float neg_inv2b) {
   float e;
   if (metric == SPB_METRIC_KL) e = (ta - tb) - dot;                            // utils.py:697 (tb = centring term c_j)
+  else if (metric == SPB_METRIC_SYMKL) e = 0.5f * ((ta + tb) - dot);             // utils.py:922-932
   else if (metric == SPB_METRIC_COS) e = fmaf(-0.5f, dot, 0.5f);               // utils.py:742
   else {
     e = fmaxf(ta + tb - 2.0f * dot, 0.0f);                                     // utils.py:780-783

@@ -93,6 +93,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ float tc_cost_to_prob(float dot, float ta, float tb, int metric, int prob_type, float neg_inv2b) {
   float e;
   if (metric == SPB_METRIC_KL) e = (ta - tb) - dot;  // tb = centring term c_j of the fixed cell
+  else if (metric == SPB_METRIC_SYMKL) e = 0.5f * ((ta + tb) - dot);             // utils.py:922-932
   else if (metric == SPB_METRIC_COS) e = fmaf(-0.5f, dot, 0.5f);
   else {
     e = fmaxf(ta + tb - 2.0f * dot, 0.0f);

@@ -87,6 +87,25 @@ def test_gene_cost_kl_matches_oracle(golden):
     assert np.abs(GT.cpu().numpy()[:, :NA] - g["exp_dist"].T).max() < 5e-6
 
 
+@pytest.mark.parametrize("backend", ["tensor", "simt"])
+def test_gene_cost_sym_kl(backend):
+    import torch
+
+    from spateo_release_b200 import _capi
+    from spateo_release_b200.alignment.morpho_class import GeneCostBuilder
+
+    rng = np.random.default_rng(0)
+    Xa = rng.poisson(1.5, size=(300, 70)).astype(np.float32)
+    Xb = rng.poisson(1.5, size=(260, 70)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    gc = GeneCostBuilder(_capi.load_library(), dev, backend=backend)
+    opA, rtA, opB, rtB, G = gc.prepare_pair(torch.from_numpy(Xa).to(dev), torch.from_numpy(Xb).to(dev), "sym_kl")
+    GT = torch.empty((260, 1024), dtype=torch.float32, device=dev)
+    gc.cost(opA, rtA, opB, rtB, 300, 260, G, "sym_kl", "prob", None, False, GT, 1024)
+    [want] = mo.calc_distance(Xa.astype(np.float64), Xb.astype(np.float64), "sym_kl")
+    assert np.abs(GT.cpu().numpy()[:, :300] - want.T).max() < 5e-6
+
+
 @pytest.mark.parametrize("metric", ["euc", "cos", "square_euc"])
 def test_gene_cost_other_metrics(metric):
     import torch
@@ -387,3 +406,42 @@ def test_spatial_sort_off_matches_on():
     assert np.abs(a.XAHat - b.XAHat).max() < 5e-6 * scale
     assert np.abs(Pa - Pb).max() < 1e-5
     assert np.abs(a.U - b.U).max() < 1e-7
+
+
+def test_label_layer_and_embedding_layers_match_oracle():
+    """Multi-layer cost: expression (KL) x label prior (obs) and an obsm embedding with cosine dissimilarity
+    (utils.py:1080-1081: probabilities of the layers multiply)."""
+    import pandas as pd
+
+    import spateo_release_b200 as st
+    from spateo_release_b200.alignment import utils as U
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(500, 460, 20, dim=2, seed=21)
+    rng = np.random.default_rng(0)
+    for ad in (A, B):
+        x = np.asarray(ad.obsm["spatial"])[:, 0]
+        lab = np.where(x < np.median(x), "left", "right")
+        ad.obs["region"] = pd.Categorical(lab, categories=["left", "right"])
+        ad.obsm["emb"] = (np.asarray(ad.X) @ rng.normal(size=(20, 6)).astype(np.float32)).astype(np.float32)
+    rng = np.random.default_rng(0)
+    for ad in (A, B):  # same projection for both slices
+        ad.obsm["emb"] = (np.asarray(ad.X) @ np.random.default_rng(5).normal(size=(20, 6))).astype(np.float32)
+    kw = dict(rep_layer=["X", "region", "emb"], rep_field=["layer", "obs", "obsm"], dissimilarity=["kl", "label", "cos"],
+              SVI_mode=False, max_iter=100, nn_init=False, verbose=False)
+    np.random.seed(0)
+    m = st.align.Morpho_pairwise(B, A, device="0", **kw)
+    m.run()
+    lt = U.check_label_transfer(B, A, "region")
+    np.random.seed(0)
+    o = mo.MorphoPairOracle(
+        np.asarray(B.obsm["spatial"]), np.asarray(A.obsm["spatial"]),
+        [m.exp_layers_A[0], m.exp_layers_A[1], m.exp_layers_A[2]], [m.exp_layers_B[0], m.exp_layers_B[1], m.exp_layers_B[2]],
+        dissimilarity=["kl", "label", "cos"], probability_type=["gauss", "prob", "gauss"], label_transfer=lt.astype(np.float64),
+        dtype="float64", SVI_mode=False, max_iter=100, nn_init=False)
+    o.run()
+    scale = np.abs(o.XAHat).max()
+    assert np.abs(m.XAHat - o.XAHat).max() / scale < 1e-3
+    assert np.abs(m.optimal_RnA - o.optimal_RnA).max() / scale < 1e-3
+    assert abs(float(m.probability_parameters[0]) - float(o.probability_parameters[0])) < 1e-3 * float(o.probability_parameters[0])
+    assert abs(float(m.probability_parameters[2]) - float(o.probability_parameters[2])) < 1e-3 * float(o.probability_parameters[2]) + 1e-6
