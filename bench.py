@@ -459,7 +459,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "aux": {"datagen_s": t_data, "construct_s": t_pre, "coarse_and_variational_init_s": t_init,
+            "aux": {"datagen_s": t_data, "construct_s": t_pre, "coarse_and_variational_init_s": t_init, "init_breakdown": getattr(m, "_timing", None),
                     "sigma2_final": float(m.sigma2), "gamma_final": float(m.gamma),
                     "chain_transforms_gathered": world},
         }

@@ -202,6 +202,13 @@ int spb_rbf_kernel_T(const float* x, int64_t n, int64_t ldx, const float* z, int
 int spb_field_eval(const double* q, int64_t n, int32_t D, const double* z, const double* Coff, int32_t K, double beta,
                    double* out, void* stream); /* transform.py:93,103; gaussian_process.py:109,117 */
 
+/* ---- coarse rigid initialisation ---------------------------------------------------------------------------------- */
+/* annealed robust Procrustes over matched pairs, 100 iterations on the device; x, y: [N][3] doubles, dist normalised,
+   P in = exp(-dist), out = closing posterior; state: 512 B scratch; out16 = R[9], t[3], sigma2, gamma (device doubles) */
+int spb_inlier_from_nn(const double* x, const double* y, const double* dist, int64_t N, int32_t D, double area, double dmin,
+                       double sigma2_init, double sumP_init, double* P, double* resid, void* state, double* out16,
+                       void* stream); /* utils.py:1220-1280 */
+
 /* ---- SparseVFC building blocks (replaces third-party dynamo scVectorField.SparseVFC; parity unpinned) ---------- */
 /* UtWU[K][K] = U^T diag(w) U and UtX[K][3] = U^T X3 (fp64 accumulation; outputs are zeroed first) */
 int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_t K, const float* w, const float* X3,

@@ -135,6 +135,7 @@ def load_library():
         "spb_optimal_rigid": ([EP, P, P], C.c_int),
         "spb_rbf_kernel_T": ([P, I64, I64, P, I32, F, P, P], C.c_int),
         "spb_field_eval": ([P, I64, I32, P, P, I32, D, P, P], C.c_int),
+        "spb_inlier_from_nn": ([P, P, P, I64, I32, D, D, D, D, P, P, P, P, P], C.c_int),
         "spb_weighted_gram": ([P, I64, I64, I32, P, P, P, P, P], C.c_int),
         "spb_vfc_estep": ([P, I64, I64, I32, I32, P, P, D, D, D, D, D, P, P, P, P, P, P], C.c_int),
         "spb_field_eval_host": ([P, I64, I32, P, P, I32, D, P], C.c_int),

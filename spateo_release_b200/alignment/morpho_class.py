@@ -463,8 +463,13 @@ class Morpho_pairwise:
         N, M, D = cA.shape[0], cB.shape[0], cA.shape[1]
         XA = U.get_rep(self.sampleA[ia], self.init_layer, self.init_field, self.genes, self._np_dtype)
         XB = U.get_rep(self.sampleB[ib], self.init_layer, self.init_field, self.genes, self._np_dtype)
+        import time as _time
+
+        _t = _time.perf_counter()
         cA, XA = U.voxel_data(cA, XA, voxel_num=max(min(int(N / 20), 1000), 100))
         cB, XB = U.voxel_data(cB, XB, voxel_num=max(min(int(M / 20), 1000), 100))
+        self._timing["coarse.voxel_data_s"] = _time.perf_counter() - _t
+        _t = _time.perf_counter()
         metric = "kl" if self.init_field == "layer" else "euc"
         ET, nA = self._raw_cost_T(XA, XB, metric)  # [nB, lds]: ET[b, a] = dist(voxel a of A, voxel b of B)
         ET = ET[:, :nA]
@@ -489,11 +494,15 @@ class Morpho_pairwise:
         NN = np.vstack((NN1, NN2))
         distance = np.r_[dist1, dist2].astype(np.float64)
         train_x, train_y = cA[NN[:, 1], :], cB[NN[:, 0], :]
-        P, R, t, _, sigma2, gamma = U.inlier_from_NN(train_x, train_y, distance[:, None])
+        self._timing["coarse.expression_knn_s"] = _time.perf_counter() - _t
+        _t = _time.perf_counter()
+        P, R, t, sigma2, gamma = self._inlier_from_NN_device(train_x, train_y, distance)
+        self._timing["coarse.inlier_from_NN_s"] = _time.perf_counter() - _t
+        self._timing["coarse.n_pairs"] = int(train_x.shape[0])
         if self.allow_flip:
             Rf = np.eye(D)
             Rf[-1, -1] = -1
-            P2, R2, t2, _, s2, g2 = U.inlier_from_NN(train_x @ Rf, train_y, distance[:, None])
+            P2, R2, t2, s2, g2 = self._inlier_from_NN_device(train_x @ Rf, train_y, distance)
             if g2 > gamma:
                 P, R, t, sigma2 = P2, R2 @ Rf, t2, s2
         thr = min(P[np.argsort(-P[:, 0])[20], 0], 0.5)
@@ -507,6 +516,31 @@ class Morpho_pairwise:
         if self.init_transform:
             self.inlier_A = self.inlier_A @ self.init_R.T + self.init_t
             self.coordsA = self.coordsA @ self.init_R.T + self.init_t
+
+    def _inlier_from_NN_device(self, train_x: np.ndarray, train_y: np.ndarray, distance: np.ndarray):
+        """``inlier_from_NN`` (utils.py:1220-1280) on the device: returns (P [N,1], R [D,D], t [D], sigma2, gamma)."""
+        dev, lib = self._dev, self._lib
+        N, D = train_x.shape
+        x64 = np.zeros((N, 3)); x64[:, :D] = train_x
+        y64 = np.zeros((N, 3)); y64[:, :D] = train_y
+        dist = np.maximum(0, np.asarray(distance, dtype=np.float64).reshape(-1))
+        dist = dist / (np.max(dist) / (np.log(10) * 2))
+        area = float(np.maximum(np.prod(train_x.max(0) - train_x.min(0)), np.prod(train_y.max(0) - train_y.min(0))))
+        sigma2_init = float(np.sum((train_x.astype(np.float64) - train_y.astype(np.float64)) ** 2) / (D * N))
+        w0 = np.exp(-dist)
+        xd, yd, dd = (torch.from_numpy(a).to(dev) for a in (x64, y64, dist))
+        Pd = torch.from_numpy(w0).to(dev)
+        resid = torch.empty((N,), dtype=torch.float64, device=dev)
+        state = torch.zeros((128,), dtype=torch.float64, device=dev)
+        out = torch.zeros((16,), dtype=torch.float64, device=dev)
+        check(
+            lib.spb_inlier_from_nn(ptr(xd), ptr(yd), ptr(dd), N, D, area, float(dist.min()), sigma2_init, float(w0.sum()),
+                                   ptr(Pd), ptr(resid), ptr(state), ptr(out), _capi.current_stream_ptr()),
+            "spb_inlier_from_nn",
+        )
+        o = out.cpu().numpy()
+        R = o[:9].reshape(3, 3)[:D, :D].copy()
+        return Pd.cpu().numpy()[:, None], R, o[9 : 9 + D].copy(), float(o[12]), float(o[13])
 
     # ------------------------------------------------------------------------------------------------------------------
     # variational initialisation (morpho_class.py:683-820; utils.py:1339-1354)
@@ -828,10 +862,19 @@ class Morpho_pairwise:
     def prepare_host(self):
         """Coarse rigid initialisation + variational initialisation (host numpy with small device helpers); consumes
         the global ``np.random`` stream in the reference's order (morpho_class.py:258-261)."""
+        import time as _time
+
+        self._timing = {}
         with torch.cuda.device(self._dev):
+            t0 = _time.perf_counter()
             if self.nn_init:
                 self._coarse_rigid_alignment()
+            torch.cuda.synchronize()
+            self._timing["coarse_rigid_alignment_s"] = _time.perf_counter() - t0
+            t0 = _time.perf_counter()
             self._initialize_variational_variables()
+            torch.cuda.synchronize()
+            self._timing["variational_init_s"] = _time.perf_counter() - t0
         self._host_ready = True
 
     def prepare_device(self):

@@ -445,3 +445,26 @@ def test_label_layer_and_embedding_layers_match_oracle():
     assert np.abs(m.optimal_RnA - o.optimal_RnA).max() / scale < 1e-3
     assert abs(float(m.probability_parameters[0]) - float(o.probability_parameters[0])) < 1e-3 * float(o.probability_parameters[0])
     assert abs(float(m.probability_parameters[2]) - float(o.probability_parameters[2])) < 1e-3 * float(o.probability_parameters[2]) + 1e-6
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_inlier_from_NN_device_matches_oracle(D):
+    """Device port of the coarse-init robust Procrustes against the oracle's float64 numpy restatement."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    rng = np.random.default_rng(4)
+    n = 5000
+    x = rng.normal(size=(n, D))
+    th = 0.6
+    R0 = np.eye(D); R0[0, 0], R0[0, 1], R0[1, 0], R0[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
+    y = x @ R0.T + 0.4 + rng.normal(0, 0.03, size=x.shape)
+    y[:600] = rng.normal(size=(600, D)) * 2.5
+    d = rng.uniform(0.01, 1.0, size=n)
+    A, B = make_slice_pair(80, 80, 6, dim=D, seed=1)
+    m = st.align.Morpho_pairwise(B, A, device="0", verbose=False, nn_init=False)
+    P, R, t, sigma2, gamma = m._inlier_from_NN_device(x, y, d)
+    Po, Ro, to, _, s2o, go = mo.inlier_from_NN(x, y, d[:, None])
+    assert np.abs(R - Ro).max() < 1e-9 and np.abs(t - to).max() < 1e-9
+    assert abs(sigma2 - s2o) < 1e-9 * s2o and abs(gamma - go) < 1e-9
+    assert np.abs(P - Po).max() < 1e-8
