@@ -69,8 +69,12 @@ def morpho_align_chain_sharded(
     pair_fn = pair_transformation if pair_fn is None else pair_fn
     local = {}
     for p in shard_pairs(n_pairs, rank, world):
-        local[p] = pair_fn(models[p], models[p + 1], spatial_key=spatial_key, **pairwise_kwargs)
-    transformation = gather_transformations(local, n_pairs, device=device)
+        kw = dict(pairwise_kwargs)
+        if device is not None and pair_fn is pair_transformation:
+            kw.setdefault("device", device)
+        local[p] = pair_fn(models[p], models[p + 1], spatial_key=spatial_key, **kw)
+    gather_dev = device if (dist.is_initialized() and dist.get_backend() == "nccl") else None
+    transformation = gather_transformations(local, n_pairs, device=gather_dev)
     models[0].obsm[key_added] = np.asarray(models[0].obsm[spatial_key]).copy()
     for i, (R, t) in enumerate(compose_transformations(transformation)):
         m = models[i + 1]

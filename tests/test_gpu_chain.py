@@ -1,0 +1,72 @@
+"""GPU: chain alignment drivers (morpho_align_transformation / apply, sharded variant, checkpoint + resume)."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _chain(n_slices=4, n=2500, g=30, seed=0):
+    """Slices that are rigid copies (plus jitter, re-sampled counts) of one base slice."""
+    import pandas as pd
+
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    rng = np.random.default_rng(seed)
+    base = rng.uniform(0, 100, size=(n, 2))
+    W = rng.normal(size=(2, g))
+    phi = rng.uniform(0, 2 * np.pi, size=g)
+    var = pd.DataFrame(index=[f"g{i}" for i in range(g)])
+    out, poses = [], []
+    for k in range(n_slices):
+        th, sh = 0.25 * k, np.array([3.0 * k, -2.0 * k])
+        perm = rng.permutation(n)
+        c = base[perm]
+        lam = np.exp(np.sin(c @ W / 30.0 + phi))
+        X = rng.poisson(lam).astype(np.float32)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+        raw = c @ R.T + sh + rng.normal(0, 0.2, size=c.shape)
+        out.append(AnnDataLite(X, var=var.copy(), obsm={"spatial": raw, "truth": c}))
+        poses.append((R, sh))
+    return out, poses
+
+
+def test_transformation_chain_recovers_poses(tmp_path):
+    import spateo_release_b200 as st
+
+    models, poses = _chain()
+    np.random.seed(0)
+    tdir = os.path.join(tmp_path, "tr")
+    tr = st.align.morpho_align_transformation(models, device="0", verbose=False, SVI_mode=False, max_iter=100,
+                                              save_transformation=True, transformation_path=tdir)
+    assert len(tr) == 3 and all(set(t) == {"Rotation", "Translation"} for t in tr)
+    assert sorted(os.listdir(tdir)) == [f"transformation_{i}.npy" for i in range(3)]
+    st.align.morpho_align_apply_transformation(models, transformation=tr)
+    ref = np.asarray(models[0].obsm["align_spatial"])
+    # every slice, mapped through the composed chain, lands on slice 0's frame: compare via the known ground truth
+    R0, s0 = poses[0]
+    for m in models[1:]:
+        want = np.asarray(m.obsm["truth"]) @ R0.T + s0
+        err = np.abs(np.asarray(m.obsm["align_spatial"]) - want)
+        assert err.mean() < 0.5 and err.max() < 3.0, (err.mean(), err.max())  # jitter 0.2 per link, domain 100
+    assert np.allclose(ref, models[0].obsm["spatial"])
+    # transformations can be re-read from the checkpoint directory
+    models2, _ = _chain()
+    st.align.morpho_align_apply_transformation(models2, transformation=None, transformation_path=tdir)
+    assert np.allclose(models2[2].obsm["align_spatial"], models[2].obsm["align_spatial"])
+
+
+def test_sharded_chain_single_process_equals_serial():
+    import spateo_release_b200 as st
+
+    models, _ = _chain(n_slices=3, n=1800)
+    np.random.seed(0)
+    tr_serial = st.align.morpho_align_transformation([m.copy() for m in models], device="0", verbose=False, SVI_mode=False, max_iter=60)
+    np.random.seed(0)
+    out, tr = st.align.morpho_align_chain_sharded([m.copy() for m in models], device="cuda:0", verbose=False, SVI_mode=False,
+                                                  max_iter=60, dtype="float32")
+    for a, b in zip(tr_serial, tr):
+        assert np.allclose(a["Rotation"], b["Rotation"], atol=1e-6) and np.allclose(a["Translation"], b["Translation"], atol=1e-4)
+    assert "align_spatial" in out[2].obsm

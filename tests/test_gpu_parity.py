@@ -468,3 +468,50 @@ def test_inlier_from_NN_device_matches_oracle(D):
     assert np.abs(R - Ro).max() < 1e-9 and np.abs(t - to).max() < 1e-9
     assert abs(sigma2 - s2o) < 1e-9 * s2o and abs(gamma - go) < 1e-9
     assert np.abs(P - Po).max() < 1e-8
+
+
+KW_VARIANTS = {
+    "large_K_eigh_path": dict(K=80, max_iter=100),
+    "update_R_false": dict(update_R=False, max_iter=90),
+    "sigma2_end": dict(sigma2_end=0.005, max_iter=90),
+    "kappa_array": dict(kappa="array", max_iter=90),
+    "separate_scale": dict(separate_scale=True, max_iter=90),
+    "no_init_transform": dict(nn_init=True, init_transform=False, max_iter=90),
+    "allow_flip": dict(nn_init=True, allow_flip=True, max_iter=90),
+    "svi_batch_size": dict(SVI_mode=True, batch_size=700, max_iter=100),
+    "robust_level": dict(partial_robust_level=50, lambdaVF=10.0, beta=0.05, max_iter=100),
+    "square_euc_cos_prob": dict(dissimilarity="cos", probability_type="cos", max_iter=90),
+}
+
+
+@pytest.mark.parametrize("name", sorted(KW_VARIANTS))
+def test_kwargs_surface_matches_oracle(name):
+    """Constructor options of Morpho_pairwise (morpho_class.py:110-167) against the float64 oracle run with the same
+    options and the same global RNG seed."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    kw = dict(SVI_mode=False, nn_init=False, verbose=False)
+    kw.update(KW_VARIANTS[name])
+    A, B = make_slice_pair(900, 800, 24, dim=2, seed=31, warp_amplitude=1.5)
+    okw = dict(kw)
+    okw.pop("verbose")
+    if kw.get("kappa") == "array":
+        kap = np.random.default_rng(0).uniform(0.5, 2.0, size=800)
+        kw["kappa"], okw["kappa"] = kap, kap
+    np.random.seed(0)
+    m = st.align.Morpho_pairwise(B, A, device="0", vecfld_key_added="vf", **kw)
+    m.run()
+    errs = {}
+    for dt in ("float32", "float64"):  # the reference's default fp32 path is the parity target; fp64 printed for scale
+        np.random.seed(0)
+        o = mo.MorphoPairOracle(np.asarray(B.obsm["spatial"]), np.asarray(A.obsm["spatial"]), [m.exp_layers_A[0]],
+                                [m.exp_layers_B[0]], dtype=dt, **okw)
+        o.run()
+        scale = np.abs(o.XAHat).max()
+        errs[dt] = (np.abs(m.XAHat - o.XAHat).max() / scale, np.abs(m.optimal_RnA - o.optimal_RnA).max() / scale,
+                    abs(float(m.sigma2) - float(o.sigma2)) / float(o.sigma2))
+    print(f"[{name}] vs fp32 oracle: nonrigid {errs['float32'][0]:.2e} rigid {errs['float32'][1]:.2e} | vs fp64 oracle: "
+          f"nonrigid {errs['float64'][0]:.2e} rigid {errs['float64'][1]:.2e}")
+    assert errs["float32"][0] < 1e-3 and errs["float32"][1] < 1e-3
+    assert errs["float32"][2] < 2e-2
