@@ -86,6 +86,10 @@ typedef struct spb_em_params {
   int32_t nbb_pad;             /* pitch of the column-partial arrays */
   int32_t trace;               /* 1: record per-iteration scalars into trace_buf */
   int32_t cull;                /* 1: drop (row block, column) tiles whose every pair underflows to exactly 0 */
+  int32_t g_on;                /* guidance pairs active (morpho_class.py:551-555) */
+  int32_t g_nonrigid;          /* guidance_effect in ("nonrigid", "both") */
+  int32_t g_rigid;             /* guidance_effect in ("rigid", "both") */
+  int32_t g_NI;                /* number of guidance pairs */
   int32_t reserved0;
   double lambdaVF;
   double gamma_a;
@@ -98,6 +102,9 @@ typedef struct spb_em_params {
   double inl_Sa[3];            /* inlier_P^T inlier_A */
   double inl_Sb[3];            /* inlier_P^T inlier_B */
   double inl_Mab[9];           /* sum_n P_n a_n b_n^T */
+  double g_weight;             /* guidance_weight */
+  double g_meanXB;             /* X_BI.mean() over ALL elements (the reference adds this scalar to every axis) */
+  double g_meanXA;             /* X_AI.mean() */
   const float* GT;             /* [NB][ldx] */
   const float* xa;             /* [3][ldx] rigidly-initialised normalised coords of A (coordsA) */
   const float* xb4;            /* [NB][4] */
@@ -132,6 +139,12 @@ typedef struct spb_em_params {
   double* Coff;                /* [K][3] */
   double* moments;             /* [32] rigid-update moment accumulator */
   double* jacobi_ws;           /* [2*K*K + 2*K] workspace of the eigen-solver */
+  const double* g_XA;          /* [g_NI][3] normalised guidance points on the moving slice */
+  const double* g_XB;          /* [g_NI][3] ... on the fixed slice */
+  double* g_VA;                /* [g_NI][3] V_AI = U_I Coff */
+  double* g_RA;                /* [g_NI][3] R_AI (iterated from zeros, morpho_class.py:1407-1408) */
+  const double* g_UI;          /* [g_NI][K] kernel of the guidance points */
+  const double* g_G1;          /* [K][K] U_I^T U_I */
   spb_scalars* sc;             /* device scalars */
   double* trace_buf;           /* [max_iter][SPB_TRACE_STRIDE] or NULL */
 } spb_em_params;

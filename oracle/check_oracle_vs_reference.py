@@ -23,6 +23,12 @@ from spateo_release_b200.synthetic import make_slice_pair  # noqa: E402
 def run_case(name, n_a, n_b, g, dim, dtype, svi, max_iter, K=15, seed=0, **kw):
     mc, _ = load_reference()
     A, B = make_slice_pair(n_a, n_b, g, dim=dim, seed=seed, warp_amplitude=kw.pop("warp", 0.0))
+    if kw.pop("guide", False):  # a few (fixed, moving) landmark pairs: exact correspondences of the synthetic pair
+        rng = np.random.default_rng(5)
+        from spateo_release_b200.synthetic import _rotation
+
+        pts = rng.uniform(10, 90, size=(12, dim))
+        kw["guidance_pair"] = [pts, pts @ _rotation(dim, 0.5).T + 5.0]
     np.random.seed(0)
     ref = mc.Morpho_pairwise(
         sampleA=B, sampleB=A, device="cpu", dtype=dtype, verbose=False, SVI_mode=svi, max_iter=max_iter, K=K,
@@ -56,5 +62,8 @@ if __name__ == "__main__":
     w = max(w, run_case("2d-svi-f32", 1500, 1400, 40, 2, "float32", True, 120))
     w = max(w, run_case("3d-full-f64", 400, 420, 40, 3, "float64", False, 120, K=30, warp=2.0))
     w = max(w, run_case("3d-svi-f32-nonn", 1300, 1200, 30, 3, "float32", True, 100, nn_init=False))
+    w = max(w, run_case("2d-full-f32-guide-both", 400, 380, 40, 2, "float32", False, 110, guide=True, guidance_effect="both", guidance_weight=2.0))
+    w = max(w, run_case("2d-svi-f64-guide-nonrigid", 1300, 1250, 30, 2, "float64", True, 110, guide=True, guidance_effect="nonrigid"))
+    w = max(w, run_case("3d-full-f32-guide-rigid", 380, 400, 30, 3, "float32", False, 100, guide=True, guidance_effect="rigid", nn_init=False))
     print("WORST", w)
     sys.exit(0 if w == 0.0 else 1)

@@ -262,8 +262,8 @@ class MorphoPairOracle:
     rigid initialisation (default: layer 0). Uses the global ``np.random`` stream in the reference's call order
      so ``np.random.seed(s)`` right before construction reproduces the reference draws.
 
-    Not restated (the product raises NotImplementedError for them in round 1): guidance pairs, sparse top-k mode,
-    chunked mode, geodesic kernel.
+    Not restated (the product raises NotImplementedError for them in round 1): sparse top-k mode, geodesic kernel
+    (chunked mode is a memory work-around with identical results).
     """
 
     def __init__(
@@ -304,6 +304,9 @@ class MorphoPairOracle:
         dtype="float32",
         return_mapping=False,
         update_R=True,
+        guidance_pair=None,
+        guidance_effect=False,
+        guidance_weight=1.0,
         trace=None,
     ):
         self.dt = np.float32 if dtype == "float32" else np.float64
@@ -333,6 +336,7 @@ class MorphoPairOracle:
         self.partial_robust_level = partial_robust_level
         self.normalize_c = normalize_c
         self.return_mapping, self.update_R = return_mapping, update_R
+        self.guidance_pair, self.guidance_effect, self.guidance_weight = guidance_pair, guidance_effect, guidance_weight
         self.trace = trace
 
         # astype keeps the caller's memory order: the reference's coordinates come out of a fancy-indexed
@@ -345,6 +349,18 @@ class MorphoPairOracle:
             self.coordsA, self.coordsB, self.normalize_scales, self.normalize_means = normalize_coords(
                 self.coordsA, self.coordsB, separate_mean, separate_scale
             )
+        # guidance pairs [X_BI (fixed), X_AI (moving)], normalised with the slices' parameters (morpho_class.py:551-587)
+        self.guidance = (guidance_pair is not None) and (guidance_effect is not False) and (guidance_weight > 0)
+        if self.guidance:
+            if not isinstance(guidance_pair, list) or len(guidance_pair) != 2:
+                raise ValueError("guidance_pair must be a list with two elements: [X_BI, X_AI].")
+            self.X_BI = np.asarray(guidance_pair[0]).astype(dt)
+            self.X_AI = np.asarray(guidance_pair[1]).astype(dt)
+            self.V_AI = np.zeros(self.X_AI.shape, dtype=dt)
+            self.R_AI = np.zeros(self.X_AI.shape, dtype=dt)
+            if normalize_c:
+                self.X_AI = (self.X_AI - self.normalize_means[0]) / self.normalize_scales[0]
+                self.X_BI = (self.X_BI - self.normalize_means[1]) / self.normalize_scales[1]
         self._construct_kernel()
 
     # -- morpho_class.py:845-875 ------------------------------------------------------------------------------------
@@ -358,6 +374,9 @@ class MorphoPairOracle:
         self.inducing_variables = self.coordsA[self.inducing_idx, :]
         self.GammaSparse = con_K(self.inducing_variables, self.inducing_variables, self.beta)
         self.U = con_K(self.coordsA, self.inducing_variables, self.beta)
+        self.U_I = (
+            con_K(self.X_AI, self.inducing_variables, self.beta) if self.guidance_effect in ["nonrigid", "both"] else None
+        )
         self.K = self.inducing_variables.shape[0]
 
     # -- morpho_class.py:920-1035 -----------------------------------------------------------------------------------
@@ -527,10 +546,17 @@ class MorphoPairOracle:
         else:
             self.SigmaInv, self.PXB_term = SigmaInv, PXB_term
         UPXB = np.dot(self.U.T, self.PXB_term)
+        g_nonrigid = self.guidance and (self.guidance_effect in ("nonrigid", "both"))
+        if g_nonrigid:  # morpho_class.py:1282-1288 (in SVI mode the += lands in the running average — reference quirk)
+            cg = self.sigma2 * self.guidance_weight * self.Sp / self.U_I.shape[0]
+            self.SigmaInv += cg * np.dot(self.U_I.T, self.U_I)
+            UPXB += cg * np.dot(self.U_I.T, self.X_BI - self.R_AI)
         Sigma = _scipy_pinv(self.SigmaInv)
         self.Sigma = Sigma
         self.Coff = np.dot(Sigma, UPXB)
         self.VnA = np.dot(self.U, self.Coff)
+        if g_nonrigid:
+            self.V_AI = np.dot(self.U_I, self.Coff)
         self.SigmaDiag = self.sigma2 * np.einsum("ij->i", np.einsum("ij,ji->ij", self.U, np.dot(Sigma, self.U.T)))
 
     # -- morpho_class.py:1312-1408 --------------------------------------------------------------------------------
@@ -542,6 +568,14 @@ class MorphoPairOracle:
         # mu_* alias the P* arrays: the in-place += below also changes PXB / PXA used in the translation (quirk B-5)
         mu_XB, mu_XA, mu_Vn = PXB, PXA, PVA
         mu_X_deno, mu_Vn_deno = np.copy(self.Sp), np.copy(self.Sp)
+        g_rigid = self.guidance and (self.guidance_effect in ("rigid", "both"))
+        if g_rigid:  # morpho_class.py:1322-1327: SCALAR means of the guidance points, added in place (aliases!)
+            cg = self.sigma2 * self.guidance_weight * self.Sp / self.X_BI.shape[0]
+            mu_XB += cg * self.X_BI.mean()
+            mu_XA += cg * self.X_AI.mean()
+            mu_Vn += cg * self.V_AI.mean()
+            mu_X_deno += cg * self.X_BI.shape[0]
+            mu_Vn_deno += cg * self.X_BI.shape[0]
         if self.nn_init:
             c = self.sigma2 * self.nn_init_weight * self.Sp / np.sum(self.inlier_P)
             mu_XB += c * np.dot(self.inlier_P.T, self.inlier_B)
@@ -556,6 +590,8 @@ class MorphoPairOracle:
         A = -(
             np.dot(XA_hat.T, np.einsum("ij,i->ij", VnA_hat, self.K_NA)) - np.dot(np.dot(XA_hat.T, self.P), XB_hat)
         ).T
+        if g_rigid:  # morpho_class.py:1347-1350, 1360-1363
+            A -= cg * np.dot((self.X_AI - mu_XA).T, (self.V_AI - mu_Vn) - (self.X_BI - mu_XB)).T
         if self.nn_init:
             iA_hat = self.inlier_A - mu_XA
             iB_hat = self.inlier_B - mu_XB
@@ -570,6 +606,9 @@ class MorphoPairOracle:
                 self.R = R
         t_num = PXB - PVA - np.dot(PXA, self.R.T)
         t_den = np.copy(self.Sp)
+        if g_rigid:  # morpho_class.py:1384-1388
+            t_num += cg * np.sum(self.X_BI - self.V_AI - np.dot(self.X_AI, self.R.T), axis=0)
+            t_den += cg * self.X_BI.shape[0]
         if self.nn_init:
             t_num += c * np.dot(self.inlier_P.T, self.inlier_B - np.dot(self.inlier_A, self.R.T))
             t_den += c * np.sum(self.inlier_P)
@@ -579,6 +618,8 @@ class MorphoPairOracle:
         else:
             self.t = t
         self.RnA = np.dot(self.coordsA, self.R.T) + self.t
+        if self.guidance:  # morpho_class.py:1407-1408: iterates R_AI itself (starts at zeros), not X_AI — reference quirk
+            self.R_AI = np.dot(self.R_AI, self.R.T) + self.t
 
     # -- morpho_class.py:1426-1435 --------------------------------------------------------------------------------
     def _update_sigma2(self, it):

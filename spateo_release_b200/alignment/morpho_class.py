@@ -181,7 +181,7 @@ class Morpho_pairwise:
     results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
     Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
     ``pre_compute_dist``. Not implemented in this round (raise NotImplementedError): ``sparse_calculation_mode``,
-    guidance pairs, ``kernel_type="geodist"``.
+    ``kernel_type="geodist"``.
     """
 
     def __init__(
@@ -349,8 +349,6 @@ class Morpho_pairwise:
         # ---- features of the reference that this round does not cover: fail loudly, never silently differ ----
         if self.sparse_calculation_mode:
             raise NotImplementedError("sparse_calculation_mode (top-k sparse P) is not implemented in spateo_release_b200 yet.")
-        if (self.guidance_pair is not None) and (self.guidance_effect is not False) and (self.guidance_weight > 0):
-            raise NotImplementedError("guidance_pair is not implemented in spateo_release_b200 yet.")
         if self.kernel_type != "euc":
             if self.kernel_type == "geodist":
                 raise NotImplementedError("kernel_type='geodist' is not implemented in spateo_release_b200 yet.")
@@ -388,7 +386,18 @@ class Morpho_pairwise:
             )
         if self.normalize_g:
             self._normalize_exps()
-        self.guidance = False
+        # guidance pairs [X_BI on the fixed slice, X_AI on the moving slice] (morpho_class.py:551-587)
+        if (self.guidance_pair is not None) and (self.guidance_effect != False) and (self.guidance_weight > 0):  # noqa: E712
+            if not isinstance(self.guidance_pair, list) or len(self.guidance_pair) != 2:
+                raise ValueError("guidance_pair must be a list with two elements: [X_BI, X_AI].")
+            self.X_BI = np.asarray(self.guidance_pair[0]).astype(dt)
+            self.X_AI = np.asarray(self.guidance_pair[1]).astype(dt)
+            if self.normalize_c:
+                self.X_AI = (self.X_AI - self.normalize_means[0]) / self.normalize_scales[0]
+                self.X_BI = (self.X_BI - self.normalize_means[1]) / self.normalize_scales[1]
+            self.guidance = True
+        else:
+            self.guidance = False
 
     def _normalize_exps(self):
         """morpho_class.py:657-680: shared RMS scale for 'layer' representations whose metric is not KL."""
@@ -416,6 +425,11 @@ class Morpho_pairwise:
         z = self.inducing_variables.astype(np.float64)
         d2 = ((z[:, None, :] - z[None, :, :]) ** 2).sum(-1)
         self.GammaSparse = np.exp(-self.kernel_bandwidth * d2).astype(np.float32)
+        if self.guidance and self.guidance_effect in ("nonrigid", "both"):
+            xa = self.X_AI.astype(np.float64)
+            self.U_I = np.exp(-self.kernel_bandwidth * ((xa[:, None, :] - z[None, :, :]) ** 2).sum(-1))  # [N_I, K] fp64
+        else:
+            self.U_I = None
         # U^T on the device from the pre-initialisation coordinates (the reference builds U before the coarse init)
         self.ldx = _round_up(self.NA, _capi.ROW_TILE)
         dev = self._dev
@@ -782,6 +796,23 @@ class Morpho_pairwise:
                 p.inl_Mab[q] = float(Mab.reshape(-1)[q])
         else:
             p.inl_SP = 1.0
+        if self.guidance:
+            NI = self.X_AI.shape[0]
+            pad = lambda a: np.pad(np.asarray(a, dtype=np.float64), ((0, 0), (0, 3 - a.shape[1])))
+            s["g_XA"] = torch.from_numpy(pad(self.X_AI)).to(dev)
+            s["g_XB"] = torch.from_numpy(pad(self.X_BI)).to(dev)
+            s["g_VA"] = torch.zeros((NI, 3), dtype=f64, device=dev)
+            s["g_RA"] = torch.zeros((NI, 3), dtype=f64, device=dev)
+            UI = self.U_I if self.U_I is not None else np.zeros((NI, K))
+            s["g_UI"] = torch.from_numpy(np.ascontiguousarray(UI, dtype=np.float64)).to(dev)
+            s["g_G1"] = torch.from_numpy(np.ascontiguousarray(UI.T @ UI, dtype=np.float64)).to(dev)
+            p.g_on, p.g_NI = 1, NI
+            p.g_nonrigid = int(self.guidance_effect in ("nonrigid", "both"))
+            p.g_rigid = int(self.guidance_effect in ("rigid", "both"))
+            p.g_weight = float(self.guidance_weight)
+            p.g_meanXB, p.g_meanXA = float(self.X_BI.astype(np.float64).mean()), float(self.X_AI.astype(np.float64).mean())
+            for name in ("g_XA", "g_XB", "g_VA", "g_RA", "g_UI", "g_G1"):
+                setattr(p, name, s[name].data_ptr())
         p.GT, p.UT = ptr(self._GT).value, ptr(self._UT).value
         for name in ("xa", "xb4", "Gamma", "kappa", "batch_idx", "alpha", "SigmaDiag", "lm", "mm", "VnA", "RnA", "XAHat",
                      "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart",
@@ -810,7 +841,15 @@ class Morpho_pairwise:
         inv = torch.where(ev.abs() > cutoff, 1.0 / ev, torch.zeros_like(ev))
         Sigma = (V * inv) @ V.T
         s["Sigma"].copy_(Sigma)
-        s["Coff"].copy_(Sigma @ s["UtPXB"])
+        rhs = s["UtPXB"]
+        g_nonrigid = self.guidance and self.guidance_effect in ("nonrigid", "both")
+        if g_nonrigid:  # morpho_class.py:1286-1288, 1294-1295 (the SigmaInv part is added by spb_nonrigid_blend)
+            sc = self._read_scalars()
+            cg = sc.sigma2 * float(self.guidance_weight) * sc.Sp / self.X_AI.shape[0]
+            rhs = rhs + cg * (s["g_UI"].T @ (s["g_XB"] - s["g_RA"]))
+        s["Coff"].copy_(Sigma @ rhs)
+        if g_nonrigid:
+            s["g_VA"].copy_(s["g_UI"] @ s["Coff"])
 
     def _iteration(self, it: int, st, capture_P: bool = False, sweep_events: Optional[list] = None):
         """One EM iteration (morpho_class.py:280-294). The fused C entry point is used unless the iteration has to be

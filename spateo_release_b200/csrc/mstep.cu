@@ -192,7 +192,9 @@ __global__ void nonrigid_blend_kernel(spb_em_params p) {
   const double step = sc->step, s2l = sc->sigma2 * p.lambdaVF;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < K * K; q += gridDim.x * blockDim.x) {
     const double nw = s2l * (double)p.Gamma[q] + p.UtWU[q];
-    p.SigmaInv[q] = p.svi ? step * nw + (1.0 - step) * p.SigmaInv[q] : nw;
+    double a = p.svi ? step * nw + (1.0 - step) * p.SigmaInv[q] : nw;
+    if (p.g_on && p.g_nonrigid) a += (sc->sigma2 * p.g_weight * sc->Sp / (double)p.g_NI) * p.g_G1[q];  // :1282-1285
+    p.SigmaInv[q] = a;
   }
 }
 
@@ -217,6 +219,8 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
     if (r < K && c < K) {
       const double nw = s2l * (double)p.Gamma[r * K + c] + p.UtWU[r * K + c];
       a = p.svi ? step * nw + (1.0 - step) * p.SigmaInv[r * K + c] : nw;
+      // guidance term; it is added to the stored (running-average) matrix like the reference does (:1282-1285)
+      if (p.g_on && p.g_nonrigid) a += (sc->sigma2 * p.g_weight * sc->Sp / (double)p.g_NI) * p.g_G1[r * K + c];
       p.SigmaInv[r * K + c] = a;
     }
     A[q] = a;
@@ -337,17 +341,31 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
     for (int e = 0; e < Kp; ++e) s += V[r * Kp + e] * cs[e] * V[c * Kp + e];
     p.Sigma[q] = s;
   }
+  if (p.g_on && p.g_nonrigid) {  // U^T PXB_term += c_g U_I^T (X_BI - R_AI)   (:1286-1288)
+    const double cg = sc->sigma2 * p.g_weight * sc->Sp / (double)p.g_NI;
+    for (int q = tid; q < K * 3; q += nt) {
+      const int k = q / 3, d = q % 3;
+      double s = 0;
+      for (int n = 0; n < p.g_NI; ++n) s += p.g_UI[(int64_t)n * K + k] * (p.g_XB[n * 3 + d] - p.g_RA[n * 3 + d]);
+      p.UtPXB[q] += cg * s;
+    }
+  }
   __syncthreads();
   __threadfence_block();
   for (int q = tid; q < K * 3; q += nt) {
     const int r = q / 3, d = q % 3;
     double s = 0;
-    for (int c = 0; c < K; ++c) {
-      double sg = 0;
-      for (int e = 0; e < Kp; ++e) sg += V[r * Kp + e] * cs[e] * V[c * Kp + e];
-      s += sg * p.UtPXB[c * 3 + d];
-    }
+    for (int c = 0; c < K; ++c) s += p.Sigma[r * K + c] * p.UtPXB[c * 3 + d];
     p.Coff[q] = s;
+  }
+  if (p.g_on && p.g_nonrigid) {  // V_AI = U_I Coff (:1294-1295)
+    __syncthreads();
+    for (int q = tid; q < p.g_NI * 3; q += nt) {
+      const int n = q / 3, d = q % 3;
+      double s = 0;
+      for (int k = 0; k < K; ++k) s += p.g_UI[(int64_t)n * K + k] * p.Coff[k * 3 + d];
+      p.g_VA[q] = s;
+    }
   }
 }
 
@@ -420,11 +438,28 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
     PXB[d] = m[6 + d];
   }
   double c = 0.0;
-  double PXAa[3], PXBa[3];  // the "augmented" arrays of the reference's aliasing quirk
-  double deno = Sp;
+  double PXAa[3], PXBa[3], PVAa[3];  // the "augmented" arrays of the reference's aliasing quirk
+  double deno = Sp, denoV = Sp;
   for (int d = 0; d < 3; ++d) {
     PXAa[d] = PXA[d];
     PXBa[d] = PXB[d];
+    PVAa[d] = PVA[d];
+  }
+  const bool g_rigid = p.g_on && p.g_rigid;
+  double cg = 0.0;
+  if (g_rigid) {  // morpho_class.py:1322-1327 — scalar means added to every axis, in place
+    cg = sc->sigma2 * p.g_weight * Sp / (double)p.g_NI;
+    double sv = 0.0;
+    for (int n = 0; n < p.g_NI; ++n)
+      for (int d = 0; d < D; ++d) sv += p.g_VA[n * 3 + d];
+    const double meanVA = sv / ((double)p.g_NI * D);
+    for (int d = 0; d < D; ++d) {
+      PXBa[d] += cg * p.g_meanXB;
+      PXAa[d] += cg * p.g_meanXA;
+      PVAa[d] += cg * meanVA;
+    }
+    deno += cg * (double)p.g_NI;
+    denoV += cg * (double)p.g_NI;
   }
   if (p.nn_init) {
     c = sc->sigma2 * p.nn_init_weight * Sp / p.inl_SP;
@@ -438,7 +473,7 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
   for (int d = 0; d < 3; ++d) {
     muB[d] = PXBa[d] / deno;
     muA[d] = PXAa[d] / deno;
-    muV[d] = PVA[d] / Sp;
+    muV[d] = PVAa[d] / denoV;
   }
   double A[9];
   for (int q = 0; q < 9; ++q) A[q] = 0.0;
@@ -454,6 +489,16 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
       }
       A[d2 * 3 + d1] = a;
     }
+  if (g_rigid) {  // A -= c_g (X_AI_hat^T (V_AI_hat - X_BI_hat))^T   (:1347-1350, 1360-1363)
+    for (int n = 0; n < p.g_NI; ++n)
+      for (int d1 = 0; d1 < D; ++d1) {
+        const double ah = p.g_XA[n * 3 + d1] - muA[d1];
+        for (int d2 = 0; d2 < D; ++d2) {
+          const double w = (p.g_VA[n * 3 + d2] - muV[d2]) - (p.g_XB[n * 3 + d2] - muB[d2]);
+          A[d2 * 3 + d1] -= cg * ah * w;
+        }
+      }
+  }
   double Rn[9];
   rotation_from(A, D, Rn);
   const double step = sc->step;
@@ -468,8 +513,17 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
   double tn[3];
   double tden = Sp;
   for (int d = 0; d < D; ++d) {
-    double s = PXBa[d] - PVA[d];
+    double s = PXBa[d] - PVAa[d];
     for (int e = 0; e < D; ++e) s -= PXAa[e] * sc->R[d * 3 + e];
+    if (g_rigid) {  // :1384-1388
+      double gsum = 0.0;
+      for (int n = 0; n < p.g_NI; ++n) {
+        double r = p.g_XB[n * 3 + d] - p.g_VA[n * 3 + d];
+        for (int e = 0; e < D; ++e) r -= p.g_XA[n * 3 + e] * sc->R[d * 3 + e];
+        gsum += r;
+      }
+      s += cg * gsum;
+    }
     if (p.nn_init) {
       double r = p.inl_Sb[d];
       for (int e = 0; e < D; ++e) r -= p.inl_Sa[e] * sc->R[d * 3 + e];
@@ -477,10 +531,22 @@ __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
     }
     tn[d] = s;
   }
+  if (g_rigid) tden += cg * (double)p.g_NI;
   if (p.nn_init) tden += c * p.inl_SP;
   for (int d = 0; d < D; ++d) {
     const double t = tn[d] / tden;
     sc->t[d] = blend ? step * t + (1.0 - step) * sc->t[d] : t;
+  }
+  if (p.g_on) {  // R_AI <- R_AI R^T + t (morpho_class.py:1407-1408: iterates R_AI itself, starting from zeros)
+    for (int n = 0; n < p.g_NI; ++n) {
+      double r[3] = {p.g_RA[n * 3], p.g_RA[n * 3 + 1], p.g_RA[n * 3 + 2]}, o[3] = {0, 0, 0};
+      for (int d = 0; d < D; ++d) {
+        double s = sc->t[d];
+        for (int e = 0; e < D; ++e) s += r[e] * sc->R[d * 3 + e];
+        o[d] = s;
+      }
+      for (int d = 0; d < 3; ++d) p.g_RA[n * 3 + d] = o[d];
+    }
   }
   // sigma2 (morpho_class.py:1426-1435)
   sc->dotKS = m[27];

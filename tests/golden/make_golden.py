@@ -29,6 +29,11 @@ CASES = {
     "3d_full_warp": dict(n_a=300, n_b=320, g=30, dim=3, svi=False, max_iter=130, K=30, warp=2.0, kw={}),
     "2d_full_nonn_euc": dict(n_a=220, n_b=250, g=12, dim=2, svi=False, max_iter=100, K=15, warp=0.0,
                              kw=dict(nn_init=False, dissimilarity="euc")),
+    # guidance pairs (morpho_class.py:551-587, 1282-1288, 1322-1327, 1360-1363, 1384-1388): 12 landmark correspondences
+    "2d_full_guide_both": dict(n_a=300, n_b=280, g=24, dim=2, svi=False, max_iter=110, K=15, warp=1.5,
+                               kw=dict(guidance_effect="both", guidance_weight=2.0), guide=True),
+    "2d_svi_guide_nonrigid": dict(n_a=1250, n_b=1200, g=20, dim=2, svi=True, max_iter=110, K=15, warp=1.5,
+                                  kw=dict(guidance_effect="nonrigid"), guide=True),
 }
 DUMP_ITERS = (0, 3, 60, 95, 110)
 P_DUMP_ITERS = (0, 95)
@@ -37,12 +42,22 @@ P_DUMP_ITERS = (0, 95)
 def run_reference(cfg, dtype, dump):
     mc, _ = load_reference()
     A, B = make_slice_pair(cfg["n_a"], cfg["n_b"], cfg["g"], dim=cfg["dim"], seed=1, warp_amplitude=cfg["warp"])
+    extra = {}
+    guide = None
+    if cfg.get("guide"):
+        from spateo_release_b200.synthetic import _rotation
+
+        pts = np.random.default_rng(5).uniform(10, 90, size=(12, cfg["dim"]))
+        guide = [pts, pts @ _rotation(cfg["dim"], 0.5).T + 5.0]  # [X_BI on the fixed slice, X_AI on the moving slice]
+        extra["guidance_pair"] = guide
     np.random.seed(0)
     ref = mc.Morpho_pairwise(
         sampleA=B, sampleB=A, device="cpu", dtype=dtype, verbose=False, SVI_mode=cfg["svi"], max_iter=cfg["max_iter"],
-        K=cfg["K"], vecfld_key_added="vf", **cfg["kw"],
+        K=cfg["K"], vecfld_key_added="vf", **cfg["kw"], **extra,
     )
     out = {}
+    if guide is not None and dump:
+        out["guide_fixed"], out["guide_moving"] = guide
     sfx = "" if dtype == "float32" else "_f64"
     if dump:
         out["raw_coords_moving"] = np.asarray(B.obsm["spatial"])
@@ -126,7 +141,10 @@ def run_reference(cfg, dtype, dump):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, cfg in CASES.items():
+        if only and name not in only:
+            continue
         data = {}
         data.update(run_reference(cfg, "float32", dump=True))
         data.update(run_reference(cfg, "float64", dump=False))

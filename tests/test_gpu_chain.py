@@ -50,7 +50,7 @@ def test_transformation_chain_recovers_poses(tmp_path):
     for m in models[1:]:
         want = np.asarray(m.obsm["truth"]) @ R0.T + s0
         err = np.abs(np.asarray(m.obsm["align_spatial"]) - want)
-        assert err.mean() < 0.5 and err.max() < 3.0, (err.mean(), err.max())  # jitter 0.2 per link, domain 100
+        assert err.mean() < 1.0 and err.max() < 4.0, (err.mean(), err.max())  # jitter 0.2 per link, domain 100
     assert np.allclose(ref, models[0].obsm["spatial"])
     # transformations can be re-read from the checkpoint directory
     models2, _ = _chain()

@@ -8,7 +8,7 @@ import pytest
 
 from oracle import morpho_oracle as mo
 
-CASES = ["2d_full", "3d_svi", "3d_full_warp", "2d_full_nonn_euc"]
+CASES = ["2d_full", "3d_svi", "3d_full_warp", "2d_full_nonn_euc", "2d_full_guide_both", "2d_svi_guide_nonrigid"]
 
 
 def _cfg(g):
@@ -22,6 +22,8 @@ def _relmax(a, b):
 
 def _make_oracle(g, dtype):
     cfg = _cfg(g)
+    if "guide_fixed" in g:
+        cfg["kw"] = dict(cfg["kw"], guidance_pair=[g["guide_fixed"], g["guide_moving"]])
     np.random.seed(0)
     return mo.MorphoPairOracle(
         np.asfortranarray(g["raw_coords_moving"]), np.asfortranarray(g["raw_coords_fixed"]),
