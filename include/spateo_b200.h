@@ -215,6 +215,30 @@ int spb_rbf_kernel_T(const float* x, int64_t n, int64_t ldx, const float* z, int
 int spb_field_eval(const double* q, int64_t n, int32_t D, const double* z, const double* Coff, int32_t K, double beta,
                    double* out, void* stream); /* transform.py:93,103; gaussian_process.py:109,117 */
 
+/* Descriptor of a fitted field (the vecfld dict of morpho_class.py:1499-1528, host side; passed by value). */
+typedef struct spb_field_desc {
+  int32_t D;
+  int32_t K;
+  int32_t nonrigid_only;
+  int32_t curvature_formula;
+  double beta;
+  double scale_transformed;
+  double scale_fixed;
+  double mean_transformed[3];
+  double mean_fixed[3];
+  double R[9];
+  double t[3];
+} spb_field_desc;
+int spb_sizeof_field_desc(void);
+/* Differential geometry of the field at n raw query points X:[n][D] (device doubles), one pass, any output may be NULL:
+   V[n][D] velocity (x_new - x)/10000, J[n][D][D] analytical Jacobian, acc[n] / acc_mat[n][D] = J v, curvature
+   (formula 1 or 2; curv_mat only for 2), curl ([n] in 2-D, [n][3] in 3-D), torsion[n][3] (3-D only), div[n], det[n].
+   z, Coff: [K][D] device doubles; f is a HOST pointer. */
+int spb_field_geometry(const spb_field_desc* f, const double* X, int64_t n, const double* z, const double* Coff,
+                       double* V, double* J, double* acc, double* acc_mat, double* curv, double* curv_mat, double* curl,
+                       double* torsion, double* div, double* det,
+                       void* stream); /* GPVectorField.py:12-125,143-190; gaussian_process.py:102-127 */
+
 /* ---- coarse rigid initialisation ---------------------------------------------------------------------------------- */
 /* annealed robust Procrustes over matched pairs, 100 iterations on the device; x, y: [N][3] doubles, dist normalised,
    P in = exp(-dist), out = closing posterior; state: 512 B scratch; out16 = R[9], t[3], sigma2, gamma (device doubles) */

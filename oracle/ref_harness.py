@@ -65,3 +65,34 @@ def load_reference():
     utils = importlib.import_module("spateo.alignment.methods.utils")
     _loaded["mc"], _loaded["utils"] = mc, utils
     return mc, utils
+
+
+def load_reference_tdr():
+    """Return (gaussian_process_module, GPVectorField_module) of the unmodified reference's st.tdr morphofield code.
+
+    ``spateo.tdr``'s package ``__init__`` pulls pyvista & co, so bare packages are registered and only the two leaf
+    modules are imported; ``numpy.matlib`` is imported first because the reference's ``_con_K(return_d=True)`` uses
+    ``np.matlib.tile`` without importing it (gaussian_process.py:28)."""
+    if "gp" in _loaded:
+        return _loaded["gp"], _loaded["gpvf"]
+    load_reference()
+    import numpy.matlib  # noqa: F401
+
+    for name, rel in [
+        ("spateo.tdr", "spateo/tdr"),
+        ("spateo.tdr.morphometrics", "spateo/tdr/morphometrics"),
+        ("spateo.tdr.morphometrics.morphofield", "spateo/tdr/morphometrics/morphofield"),
+        ("spateo.tdr.morphometrics.morphofield_dg", "spateo/tdr/morphometrics/morphofield_dg"),
+    ]:
+        if name not in sys.modules:
+            pkg = types.ModuleType(name)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, rel)]
+            sys.modules[name] = pkg
+    if "spateo.tdr.interpolations" not in sys.modules:
+        interp = types.ModuleType("spateo.tdr.interpolations")
+        interp.get_X_Y_grid = lambda *a, **k: None
+        sys.modules["spateo.tdr.interpolations"] = interp
+    gp = importlib.import_module("spateo.tdr.morphometrics.morphofield.gaussian_process")
+    gpvf = importlib.import_module("spateo.tdr.morphometrics.morphofield_dg.GPVectorField")
+    _loaded["gp"], _loaded["gpvf"] = gp, gpvf
+    return gp, gpvf

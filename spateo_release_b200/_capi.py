@@ -69,6 +69,10 @@ class SpbEmParams(C.Structure):
     _fields_ = _parse_struct(_hdr, "spb_em_params")
 
 
+class SpbFieldDesc(C.Structure):
+    _fields_ = _parse_struct(_hdr, "spb_field_desc")
+
+
 def _consts():
     out = {}
     for k, v in re.findall(r"#define (SPB_[A-Z_0-9]+)\s+\(?(-?\d+)\)?", _hdr):
@@ -107,6 +111,7 @@ def load_library():
         "spb_launch_count": ([], C.c_int64),
         "spb_sizeof_em_params": ([], C.c_int),
         "spb_sizeof_scalars": ([], C.c_int),
+        "spb_sizeof_field_desc": ([], C.c_int),
         "spb_kl_prepare_rows": ([P, I64, I64, I64, P, I64, P, I32, P, P], C.c_int),
         "spb_rows_sqnorm": ([P, I64, I64, I64, P, P], C.c_int),
         "spb_rows_normalize": ([P, I64, I64, I64, P, I64, P], C.c_int),
@@ -135,6 +140,7 @@ def load_library():
         "spb_optimal_rigid": ([EP, P, P], C.c_int),
         "spb_rbf_kernel_T": ([P, I64, I64, P, I32, F, P, P], C.c_int),
         "spb_field_eval": ([P, I64, I32, P, P, I32, D, P, P], C.c_int),
+        "spb_field_geometry": ([C.POINTER(SpbFieldDesc), P, I64, P, P, P, P, P, P, P, P, P, P, P, P, P], C.c_int),
         "spb_inlier_from_nn": ([P, P, P, I64, I32, D, D, D, D, P, P, P, P, P], C.c_int),
         "spb_weighted_gram": ([P, I64, I64, I32, P, P, P, P, P], C.c_int),
         "spb_vfc_estep": ([P, I64, I64, I32, I32, P, P, D, D, D, D, D, P, P, P, P, P, P], C.c_int),
@@ -145,7 +151,8 @@ def load_library():
         fn.argtypes = argtypes
         fn.restype = restype
     lib._spb_signatures = sig
-    if lib.spb_sizeof_em_params() != C.sizeof(SpbEmParams) or lib.spb_sizeof_scalars() != C.sizeof(SpbScalars):
+    if lib.spb_sizeof_em_params() != C.sizeof(SpbEmParams) or lib.spb_sizeof_scalars() != C.sizeof(SpbScalars) or \
+            lib.spb_sizeof_field_desc() != C.sizeof(SpbFieldDesc):
         raise SpbError("struct layout mismatch between include/spateo_b200.h and the built library: rebuild it")
     _lib = lib
     return lib

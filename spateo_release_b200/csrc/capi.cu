@@ -13,3 +13,4 @@ extern "C" int spb_version(void) { return 100; }
 
 extern "C" int spb_sizeof_em_params(void) { return (int)sizeof(spb_em_params); }
 extern "C" int spb_sizeof_scalars(void) { return (int)sizeof(spb_scalars); }
+extern "C" int spb_sizeof_field_desc(void) { return (int)sizeof(spb_field_desc); }
