@@ -90,7 +90,7 @@ typedef struct spb_em_params {
   int32_t g_nonrigid;          /* guidance_effect in ("nonrigid", "both") */
   int32_t g_rigid;             /* guidance_effect in ("rigid", "both") */
   int32_t g_NI;                /* number of guidance pairs */
-  int32_t reserved0;
+  int32_t sparse_k;            /* > 0: sparse_calculation_mode with sparse_top_k = sparse_k (utils.py:1085-1094) */
   double lambdaVF;
   double gamma_a;
   double gamma_b;
@@ -126,7 +126,7 @@ typedef struct spb_em_params {
   float* PXB_term;             /* [3][ldx] (SVI running average) */
   float* K_NB;                 /* [NBb] */
   float* colgeom;              /* [nbb_pad][8] (y0,y0,y1,y1,y2,y2,0,0): this iteration's columns, duplicated for f32x2 */
-  float* colconst;             /* [nbb_pad][16] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, 0,0,0,0); zero beyond NBb */
+  float* colconst;             /* [nbb_pad][16] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, tau,tau,0,0); zero beyond NBb */
   float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
   float* rowpart;              /* [seg2][8][ldx] partial row statistics */
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
@@ -190,6 +190,18 @@ int spb_col_finalize(const spb_em_params* p, void* stream);               /* uti
 int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1059-1083, morpho_class.py:1171-1176,1270,1357 */
 int spb_row_finalize(const spb_em_params* p, void* stream);
 /* dense P [NA][NBb] (row-major, pitch ldp) of the state left by the last E-step */
+/* sparse_calculation_mode (p->sparse_k > 0): per-column top-k threshold tau_j of the full posterior by an exact radix
+   select (one CTA per column), written to colconst[j][12..13]; K_NB_j becomes the kept mass. Call between
+   spb_col_finalize and spb_estep_sweep2 (spb_em_iteration does). */
+int spb_estep_col_select(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1085-1094,1369-1404 */
+/* COO entries of the sparse posterior of the last E-step: rows[NBb][sparse_k], vals[NBb][sparse_k] (unordered inside a
+   column; columns with fewer than sparse_k non-zero entries are filled with explicit zeros like the reference's sort) */
+int spb_sparse_P_emit(const spb_em_params* p, int32_t iter, int32_t* rows, float* vals, void* stream); /* utils.py:1385-1392,1506-1510 */
+/* Row / column maxima of the posterior of the last E-step without forming it: rowbest[NA], colbest[NBb] hold
+   (float bits of P) << 32 | (0xffffffff - argmax index) — lowest index on ties; either pointer may be NULL.
+   In sparse mode entries below a column's top-k threshold count as absent (0), as in the reference's sparse pi. */
+int spb_posterior_argmax(const spb_em_params* p, int32_t iter, uint64_t* rowbest, uint64_t* colbest,
+                         void* stream); /* spateo/alignment/utils.py:157-191 (get_optimal_mapping_relationship) */
 int spb_materialize_P(const spb_em_params* p, int32_t iter, float* P, int64_t ldp, void* stream); /* utils.py:1083 */
 
 /* ---- M-step pieces ---------------------------------------------------------------------------------------------- */

@@ -47,8 +47,11 @@ def run_case(name, n_a, n_b, g, dim, dtype, svi, max_iter, K=15, seed=0, **kw):
     P_orc = orc.run()
     worst = 0.0
     for key in ["P", "optimal_RnA", "XAHat", "RnA", "R", "t", "Coff", "sigma2", "gamma", "optimal_R", "optimal_t"]:
-        a = np.asarray(getattr(ref, key), dtype=np.float64)
-        b = np.asarray(getattr(orc, key), dtype=np.float64)
+        a, b = getattr(ref, key), getattr(orc, key)
+        if hasattr(a, "toarray"):  # sparse_calculation_mode returns scipy COO
+            a, b = a.toarray(), b.toarray()
+        a = np.asarray(a, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
         d = np.abs(a - b).max() / max(np.abs(a).max(), 1e-30)
         worst = max(worst, d)
         print(f"  {key:12s} shape={a.shape} max-rel-dev={d:.3e}")
@@ -65,5 +68,7 @@ if __name__ == "__main__":
     w = max(w, run_case("2d-full-f32-guide-both", 400, 380, 40, 2, "float32", False, 110, guide=True, guidance_effect="both", guidance_weight=2.0))
     w = max(w, run_case("2d-svi-f64-guide-nonrigid", 1300, 1250, 30, 2, "float64", True, 110, guide=True, guidance_effect="nonrigid"))
     w = max(w, run_case("3d-full-f32-guide-rigid", 380, 400, 30, 3, "float32", False, 100, guide=True, guidance_effect="rigid", nn_init=False))
+    w = max(w, run_case("2d-full-f32-sparse64", 400, 380, 40, 2, "float32", False, 110, sparse_calculation_mode=True, sparse_top_k=64))
+    w = max(w, run_case("3d-svi-f32-sparse32", 1300, 1200, 30, 3, "float32", True, 100, sparse_calculation_mode=True, sparse_top_k=32))
     print("WORST", w)
     sys.exit(0 if w == 0.0 else 1)

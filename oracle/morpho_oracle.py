@@ -111,8 +111,13 @@ def get_P_core(
     probability_type=("gauss",),
     probability_parameters=None,
     eps=1e-8,
+    sparse_calculation_mode=False,
+    top_k=-1,
 ):
     """Three column-normalised posteriors sharing one spatial distance block (utils.py:1049-1083).
+
+    ``sparse_calculation_mode`` keeps the ``top_k`` largest entries of every column of the full posterior as a scipy COO
+    matrix (utils.py:1085-1094 -> _dense_to_sparse, utils.py:1369-1404); the other two posteriors stay dense.
 
     Returns (P, K_NA_spatial, K_NA_sigma2, sigma2_related_numerator).
     """
@@ -135,7 +140,36 @@ def get_P_core(
     for e_d, p_t, p_p in zip(exp_dist, probability_type, probability_parameters):
         sp *= calc_probability(e_d, p_t, p_p)
     P = inlier * sp / (sp.sum(axis=0, keepdims=True) + eps)
+    if sparse_calculation_mode:
+        P = dense_to_sparse_topk(P, top_k)
     return P, K_NA_spatial, K_NA_sigma2, sigma2_related
+
+
+def dense_to_sparse_topk(mat, threshold):
+    """utils.py:1369-1404 with sparse_method="topk", axis=0, descending=True (numpy backend: sort2 of the negated matrix,
+    backend.py:1138-1142; COO assembly utils.py:1506-1510 with float column indices from ``nx.arange(type_as=mat)``)."""
+    import scipy.sparse as sp
+
+    NA, NB = mat.shape
+    threshold = int(threshold)
+    sorted_mat, sorted_idx = -np.sort(-mat, axis=0), np.argsort(-mat, axis=0)
+    if threshold > NA:
+        threshold = NA
+    col = np.repeat(np.arange(NB).astype(mat.dtype), threshold, axis=0)
+    row = sorted_idx[:threshold, :].T.reshape(-1)
+    val = sorted_mat[:threshold, :].T.reshape(-1)
+    return sp.coo_matrix((val, (row, col)), shape=(NA, NB))
+
+
+def _dot(a, b):
+    """NumpyBackend.dot (backend.py:1082-1091): scipy-sparse aware."""
+    import scipy.sparse as sp
+
+    if sp.issparse(a):
+        return a.dot(b)
+    if sp.issparse(b):
+        return b.T.dot(a.T).T
+    return np.dot(a, b)
 
 
 def con_K(X, Y, beta=0.01):
@@ -308,7 +342,10 @@ class MorphoPairOracle:
         guidance_effect=False,
         guidance_weight=1.0,
         trace=None,
+        sparse_calculation_mode=False,
+        sparse_top_k=1024,
     ):
+        self.sparse_calculation_mode, self.sparse_top_k = sparse_calculation_mode, sparse_top_k
         self.dt = np.float32 if dtype == "float32" else np.float64
         dt = self.dt
         self.f = lambda v: np.asarray(v, dtype=dt)  # the reference's _data(nx, v, type_as)
@@ -330,6 +367,8 @@ class MorphoPairOracle:
         self.nn_init_top_K, self.nn_init_weight = nn_init_top_K, nn_init_weight
         self.max_iter, self.nonrigid_start_iter = max_iter, nonrigid_start_iter
         self.SVI_mode, self.batch_size, self.pre_compute_dist = SVI_mode, batch_size, pre_compute_dist
+        if sparse_calculation_mode:  # morpho_class.py:439-440
+            self.pre_compute_dist = False
         self.lambdaVF, self.beta, self.K = lambdaVF, beta, K
         self.sigma2_init_scale, self.sigma2_end = sigma2_init_scale, sigma2_end
         self.gamma_a, self.gamma_b, self.kappa = gamma_a, gamma_b, kappa
@@ -504,12 +543,17 @@ class MorphoPairOracle:
             sigma2_variance=self.sigma2_variance,
             probability_type=self.probability_type,
             probability_parameters=self.probability_parameters,
+            sparse_calculation_mode=self.sparse_calculation_mode,
+            top_k=self.sparse_top_k,
         )
         Sp = self.P.sum()
         Sp_sigma2 = self.K_NA_sigma2.sum()
         Sp_spatial = self.K_NA_spatial.sum()
         self.K_NA = self.P.sum(axis=1)
         self.K_NB = self.P.sum(axis=0)
+        if self.sparse_calculation_mode:  # morpho_class.py:1187-1198 (scipy returns np.matrix)
+            self.K_NA = np.asarray(self.K_NA).squeeze(-1)
+            self.K_NB = np.asarray(self.K_NB).squeeze(0)
         if self.SVI_mode:
             s = self.step_size
             self.Sp_spatial = s * Sp_spatial + (1 - s) * self.Sp_spatial
@@ -538,7 +582,7 @@ class MorphoPairOracle:
             self.U.T, np.einsum("ij,i->ij", self.U, self.K_NA)
         )
         YB = self.coordsB[self.batch_idx, :] if self.SVI_mode else self.coordsB
-        PXB_term = np.dot(self.P, YB) - np.einsum("ij,i->ij", self.RnA, self.K_NA)
+        PXB_term = _dot(self.P, YB) - np.einsum("ij,i->ij", self.RnA, self.K_NA)
         if self.SVI_mode:
             s = self.step_size
             self.SigmaInv = s * SigmaInv + (1 - s) * self.SigmaInv
@@ -588,7 +632,7 @@ class MorphoPairOracle:
         VnA_hat = self.VnA - mu_Vn
         XB_hat = YB - mu_XB
         A = -(
-            np.dot(XA_hat.T, np.einsum("ij,i->ij", VnA_hat, self.K_NA)) - np.dot(np.dot(XA_hat.T, self.P), XB_hat)
+            np.dot(XA_hat.T, np.einsum("ij,i->ij", VnA_hat, self.K_NA)) - np.dot(_dot(XA_hat.T, self.P), XB_hat)
         ).T
         if g_rigid:  # morpho_class.py:1347-1350, 1360-1363
             A -= cg * np.dot((self.X_AI - mu_XA).T, (self.V_AI - mu_Vn) - (self.X_BI - mu_XB)).T
@@ -635,7 +679,7 @@ class MorphoPairOracle:
         YB = self.coordsB[self.batch_idx, :] if self.SVI_mode else self.coordsB
         mu_A = np.dot(self.K_NA, self.coordsA) / self.Sp
         mu_B = np.dot(self.K_NB, YB) / self.Sp
-        A = np.dot(np.dot(self.P, YB - mu_B).T, self.coordsA - mu_A)
+        A = np.dot(_dot(self.P, YB - mu_B).T, self.coordsA - mu_A)
         svdU, _, svdV = np.linalg.svd(A)
         self.C[-1, -1] = np.linalg.det(np.dot(svdU, svdV))
         self.optimal_R = np.dot(np.dot(svdU, self.C), svdV)

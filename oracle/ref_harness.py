@@ -96,3 +96,12 @@ def load_reference_tdr():
     gpvf = importlib.import_module("spateo.tdr.morphometrics.morphofield_dg.GPVectorField")
     _loaded["gp"], _loaded["gpvf"] = gp, gpvf
     return gp, gpvf
+
+
+def load_reference_align_utils():
+    """The unmodified ``spateo/alignment/utils.py`` (get_optimal_mapping_relationship, mapping_aligned_coords)."""
+    if "au" in _loaded:
+        return _loaded["au"]
+    load_reference()
+    _loaded["au"] = importlib.import_module("spateo.alignment.utils")
+    return _loaded["au"]

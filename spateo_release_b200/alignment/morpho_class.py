@@ -176,11 +176,14 @@ class Morpho_pairwise:
 
     Extra keywords (not in the reference): ``materialize_P`` — when False ``run()`` skips building the dense
     N_A x N_B posterior (40 GB at 100k x 100k) and returns None; every other output is unaffected.
+    ``compute_mapping`` — ``self.mapping`` (an ``ArgmaxPi``) receives the row / column maxima of the final posterior from a
+    fused kernel, for ``get_optimal_mapping_relationship`` / ``mapping_aligned_coords`` without a dense P.
     ``spatial_sort`` / ``cull_zero_tiles`` — the moving cells are processed in Morton order so that each 1024-row block is
     spatially compact, and (row block, fixed cell) tiles whose every pair underflows to exactly 0 in fp32 are skipped;
     results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
     Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
-    ``pre_compute_dist``. Not implemented in this round (raise NotImplementedError): ``sparse_calculation_mode``,
+    ``pre_compute_dist``. ``sparse_calculation_mode`` keeps the top ``sparse_top_k`` posterior entries of every column by an
+    exact on-device radix select (P comes back as ``scipy.sparse.coo_matrix``). Not implemented (NotImplementedError):
     ``kernel_type="geodist"``.
     """
 
@@ -242,6 +245,7 @@ class Morpho_pairwise:
         return_mapping: bool = False,
         update_R: bool = True,
         materialize_P: bool = True,
+        compute_mapping: bool = False,
         spatial_sort: bool = True,
         cull_zero_tiles: bool = True,
     ) -> None:
@@ -274,6 +278,7 @@ class Morpho_pairwise:
         self.nonrigid_start_iter = nonrigid_start_iter
         self.return_mapping, self.update_R = return_mapping, update_R
         self.materialize_P = materialize_P
+        self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64
@@ -348,7 +353,9 @@ class Morpho_pairwise:
                 )
         # ---- features of the reference that this round does not cover: fail loudly, never silently differ ----
         if self.sparse_calculation_mode:
-            raise NotImplementedError("sparse_calculation_mode (top-k sparse P) is not implemented in spateo_release_b200 yet.")
+            self.pre_compute_dist = False  # morpho_class.py:439-440 (no effect here: the cost matrix is always resident)
+            if int(self.sparse_top_k) < 1:
+                raise ValueError("sparse_top_k must be a positive integer.")
         if self.kernel_type != "euc":
             if self.kernel_type == "geodist":
                 raise NotImplementedError("kernel_type='geodist' is not implemented in spateo_release_b200 yet.")
@@ -776,6 +783,7 @@ class Morpho_pairwise:
         p.nonrigid_start_iter = int(self.nonrigid_start_iter)
         p.seg1, p.seg2, p.nbb_pad, p.trace = seg1, seg2, self._nbb_pad, 1
         p.cull = int(bool(self.cull_zero_tiles))
+        p.sparse_k = int(self.sparse_top_k) if self.sparse_calculation_mode else 0
         p.lambdaVF, p.gamma_a, p.gamma_b = float(self.lambdaVF), float(self.gamma_a), float(self.gamma_b)
         p.samples_s = float(self.samples_s)
         p.nn_init_weight = float(self.nn_init_weight)
@@ -863,8 +871,7 @@ class Morpho_pairwise:
             return
         self._estep_only(it, st, sweep_events)
         if capture_P:
-            self._P_dev = torch.empty((self.NA, self._NBb), dtype=torch.float32, device=self._dev)
-            check(lib.spb_materialize_P(C.byref(p), it, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
+            self._capture_P(it, st)
         check(lib.spb_update_gamma_alpha(C.byref(p), st), "spb_update_gamma_alpha")
         if nonrigid:
             check(lib.spb_nonrigid_accumulate(C.byref(p), st), "spb_nonrigid_accumulate")
@@ -876,6 +883,41 @@ class Morpho_pairwise:
         check(lib.spb_rigid_moments(C.byref(p), st), "spb_rigid_moments")
         check(lib.spb_rigid_solve(C.byref(p), it, st), "spb_rigid_solve")
         check(lib.spb_row_update(C.byref(p), st), "spb_row_update")
+
+    def _capture_P(self, it: int, st):
+        """Posterior of the E-step that has just run: dense [N_A, NBb], or in sparse_calculation_mode the COO entries
+        (top-k rows and values per column) without ever forming the dense matrix."""
+        lib, p = self._lib, self._params
+        if self.compute_mapping:  # row / column maxima of the same posterior, straight from the cost matrix
+            self._rowbest = torch.zeros((self.NA,), dtype=torch.int64, device=self._dev)
+            self._colbest = torch.zeros((self._NBb,), dtype=torch.int64, device=self._dev)
+            check(lib.spb_posterior_argmax(C.byref(p), it, ptr(self._rowbest), ptr(self._colbest), st), "spb_posterior_argmax")
+        if not self.materialize_P:
+            self._P_dev = "skipped"
+            return
+        if self.sparse_calculation_mode:
+            k = int(self.sparse_top_k)
+            self._P_rows = torch.zeros((self._NBb, k), dtype=torch.int32, device=self._dev)
+            self._P_vals = torch.zeros((self._NBb, k), dtype=torch.float32, device=self._dev)
+            check(lib.spb_sparse_P_emit(C.byref(p), it, ptr(self._P_rows), ptr(self._P_vals), st), "spb_sparse_P_emit")
+            self._P_dev = "sparse"
+        else:
+            self._P_dev = torch.empty((self.NA, self._NBb), dtype=torch.float32, device=self._dev)
+            check(lib.spb_materialize_P(C.byref(p), it, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
+
+    def _sparse_P_to_coo(self, dt):
+        """scipy COO in the reference's layout (utils.py:1385-1392,1506-1510): per column the k entries in descending
+        order, columns concatenated."""
+        import scipy.sparse as sp
+
+        k = min(int(self.sparse_top_k), self.NA)
+        vals, order = torch.sort(self._P_vals[:, :k], dim=1, descending=True, stable=True)
+        rows = torch.gather(self._P_rows[:, :k].long(), 1, order).cpu().numpy()
+        if self._perm is not None:
+            rows = self._perm[rows]
+        col = np.repeat(np.arange(self._NBb), k)
+        return sp.coo_matrix((vals.cpu().numpy().astype(dt).reshape(-1), (rows.reshape(-1), col)),
+                             shape=(self.NA, self._NBb))
 
     def _estep_only(self, it: int, st, sweep_events: Optional[list] = None):
         """One E-step + the statistics the closing similarity needs (used for return_mapping under SVI)."""
@@ -890,6 +932,8 @@ class Morpho_pairwise:
         if sweep_events is not None:
             e1.record()
         check(lib.spb_col_finalize(C.byref(p), st), "spb_col_finalize")
+        if self.sparse_calculation_mode:
+            check(lib.spb_estep_col_select(C.byref(p), it, st), "spb_estep_col_select")
         if sweep_events is not None:
             e2.record()
         check(lib.spb_estep_sweep2(C.byref(p), it, st), "spb_estep_sweep2")
@@ -951,7 +995,7 @@ class Morpho_pairwise:
                     hist[it].copy_(self._state["XAHat"])
                     self._state["hist_sigma2"][it].copy_(self._state["sc"][:8].view(torch.float64)[0])
                 last = it == self.max_iter - 1
-                want_P = self.materialize_P and last and not (self.return_mapping and self.SVI_mode)
+                want_P = (self.materialize_P or self.compute_mapping) and last and not (self.return_mapping and self.SVI_mode)
                 self._iteration(it, st, capture_P=want_P, sweep_events=sweep_events)
 
     @torch.no_grad()
@@ -1031,14 +1075,26 @@ class Morpho_pairwise:
         else:
             self.Coff = np.zeros(self.K, dtype=dt)  # the reference's initial value (morpho_class.py:733)
         self.trace = s["trace_buf"].cpu().numpy()
+        if (self.materialize_P or self.compute_mapping) and getattr(self, "_P_dev", None) is None:
+            self._capture_P(last_iter, st)  # max_iter == 0 or the return_mapping E-step above
+        if self.compute_mapping:
+            from .mapping import ArgmaxPi
+
+            ra, rv = ArgmaxPi.decode(self._rowbest.cpu().numpy().view(np.uint64))
+            ca, cv = ArgmaxPi.decode(self._colbest.cpu().numpy().view(np.uint64))
+            if self._perm is not None:  # device rows are in processing order
+                ra, rv, ca = self._unsorted(ra), self._unsorted(rv), self._perm[ca]
+            self.mapping = ArgmaxPi((NA, self._NBb), ra, rv.astype(dt), ca, cv.astype(dt))
+            self._rowbest = self._colbest = None
         if self.materialize_P:
-            if getattr(self, "_P_dev", None) is None:  # max_iter == 0 or the return_mapping E-step above
-                self._P_dev = torch.empty((NA, self._NBb), dtype=torch.float32, device=self._dev)
-                check(lib.spb_materialize_P(C.byref(p), last_iter, ptr(self._P_dev), self._NBb, st), "spb_materialize_P")
-            self.P = self._unsorted(self._P_dev.cpu().numpy().astype(dt))
-            self._P_dev = None
+            if self.sparse_calculation_mode:
+                self.P = self._sparse_P_to_coo(dt)
+                self._P_rows = self._P_vals = None
+            else:
+                self.P = self._unsorted(self._P_dev.cpu().numpy().astype(dt))
         else:
             self.P = None
+        self._P_dev = None
         if self.iter_key_added is not None:
             hist = s["hist"][:, :D, :NA].permute(0, 2, 1).contiguous().cpu().numpy().astype(dt)
             if self._perm is not None:

@@ -261,7 +261,15 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 2: row statistics
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kColStage, int kStages, int kMinBlocks>
+// kSparse (sparse_calculation_mode, utils.py:1085-1094): only pairs whose weight q g reaches the column's top-k threshold
+// tau_j (col_select_kernel) enter K_NA and P @ XB; the spatial and sigma2 posteriors stay dense as in the reference.
+__device__ __forceinline__ u64 keep_ge(u64 w, float tau) {
+  float a, b;
+  upk(w, a, b);
+  return pk(a >= tau ? a : 0.f, b >= tau ? b : 0.f);
+}
+
+template <int kColStage, int kStages, int kMinBlocks, bool kSparse>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
@@ -321,7 +329,13 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
       s2b = add2(s2b, tb);
       sda = fma2(ta, da, sda);
       sdb = fma2(tb, db, sdb);
-      const u64 pa = mul2(mul2(qa, g.x), c2.y), pb = mul2(mul2(qb, g.y), c2.y);
+      u64 wa = mul2(qa, g.x), wb = mul2(qb, g.y);
+      if constexpr (kSparse) {
+        const float tau = sm.cols[s][jj][3].x;
+        wa = keep_ge(wa, tau);
+        wb = keep_ge(wb, tau);
+      }
+      const u64 pa = mul2(wa, c2.y), pb = mul2(wb, c2.y);
       ka = add2(ka, pa);
       kb = add2(kb, pb);
       pxa = fma2(pa, c0.x, pxa);
@@ -510,6 +524,308 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sparse_calculation_mode: per-column top-k of the full posterior (utils.py:1085-1094 -> _dense_to_sparse :1369-1404)
+// ---------------------------------------------------------------------------------------------------------------------
+// Within a column P_ij = w_ij c_j with w = q g, so the k largest P are the k largest w. One CTA owns one column (its GT
+// row is contiguous) and finds the k-th largest w EXACTLY by a 3-level radix select on the float bits (12 + 12 + 7 bits;
+// w >= 0 so the bit pattern is monotone). After the first level the surviving candidates are gathered into shared
+// memory, so the column is normally read twice. Per-bin sums give the kept mass without another pass:
+//   tau_j   -> colconst[j][12..13]  (sweep 2 keeps pairs with w >= tau_j; exact ties at tau_j are all kept)
+//   K_NB_j  = c_j * sum_{w >= tau_j} w
+// The weight is evaluated with the same instruction sequence as the packed sweep (sub, mul, fma, fma, fma, ex2, mul), so
+// both kernels see bit-identical w.
+constexpr int kSelThreads = 512;
+constexpr int kSelBins = 4096;
+constexpr int kSelCap = 8192;
+
+__device__ __forceinline__ float pair_weight(float x0, float x1, float x2, float y0, float y1, float y2, float cq,
+                                             float lmi, float g) {
+  const float d0 = __fsub_rn(x0, y0), d1 = __fsub_rn(x1, y1), d2 = __fsub_rn(x2, y2);
+  const float d = __fmaf_rn(d2, d2, __fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+  return __fmul_rn(ex2f(__fmaf_rn(cq, d, lmi)), g);
+}
+
+struct SelShared {
+  uint32_t wcnt[kSelThreads / 32];
+  float wsum[kSelThreads / 32];
+  uint32_t bsel, above_cnt, sel_cnt, total;
+  float above_sum, sel_sum, total_sum;
+  int ncand;
+};
+
+// histogram of (key >> shift) & (nb - 1) over the values whose key matches (prefix, pmask); zero weights are skipped
+template <typename F>
+__device__ __forceinline__ void sel_for_each(const float* __restrict__ g, const float* __restrict__ XA, int64_t ldx,
+                                             const float* __restrict__ lm, int NA, float y0, float y1, float y2, float cq,
+                                             F&& f) {
+  for (int i = threadIdx.x * 4; i < NA; i += kSelThreads * 4) {
+    const float4 G = *reinterpret_cast<const float4*>(g + i);
+    const float4 X0 = *reinterpret_cast<const float4*>(XA + i);
+    const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + i);
+    const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + i);
+    const float4 L = *reinterpret_cast<const float4*>(lm + i);
+    f(i, pair_weight(X0.x, X1.x, X2.x, y0, y1, y2, cq, L.x, G.x));
+    if (i + 1 < NA) f(i + 1, pair_weight(X0.y, X1.y, X2.y, y0, y1, y2, cq, L.y, G.y));
+    if (i + 2 < NA) f(i + 2, pair_weight(X0.z, X1.z, X2.z, y0, y1, y2, cq, L.z, G.z));
+    if (i + 3 < NA) f(i + 3, pair_weight(X0.w, X1.w, X2.w, y0, y1, y2, cq, L.w, G.w));
+  }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+                  float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
+                  const spb_scalars* __restrict__ sc, int NA, int topk, float* __restrict__ K_NB) {
+  extern __shared__ __align__(16) uint8_t sel_raw[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(sel_raw);
+  float* sums = reinterpret_cast<float*>(hist + kSelBins);
+  float* cand = sums + kSelBins;
+  __shared__ SelShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jb = blockIdx.x;
+  float* cc = colconst + (int64_t)jb * 16;
+  const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
+  const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
+  const float* g = GT + row * ldx;
+  const float cq = sc->c_q;
+  uint32_t prefix = 0, pmask = 0, remaining = (uint32_t)min(topk, NA);
+  float kept = 0.f;
+  bool use_cand = false;
+  int ncand = 0;
+  float tau = 0.f;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 19 : (pass == 1 ? 7 : 0);
+    const int nb = pass == 2 ? 128 : kSelBins;
+    for (int t = tid; t < nb; t += kSelThreads) {
+      hist[t] = 0u;
+      sums[t] = 0.f;
+    }
+    __syncthreads();
+    auto add = [&](int, float w) {
+      const uint32_t key = __float_as_uint(w);
+      if (key != 0u && (key & pmask) == prefix) {
+        const uint32_t b = (key >> shift) & (uint32_t)(nb - 1);
+        atomicAdd(&hist[b], 1u);
+        atomicAdd(&sums[b], w);
+      }
+    };
+    if (!use_cand) {
+      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, add);
+    } else {
+      for (int t = tid; t < ncand; t += kSelThreads) add(t, cand[t]);
+    }
+    __syncthreads();
+    // suffix scan over bins (high bins first): thread t owns bins [t * per, (t + 1) * per)
+    const int per = nb >= kSelThreads ? nb / kSelThreads : 1;
+    const bool owner = tid * per < nb;
+    uint32_t mycnt = 0;
+    float mysum = 0.f;
+    if (owner)
+      for (int q = 0; q < per; ++q) {
+        mycnt += hist[tid * per + q];
+        mysum += sums[tid * per + q];
+      }
+    uint32_t c = mycnt;
+    float sm_ = mysum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t c2 = __shfl_down_sync(0xffffffffu, c, off);
+      const float s2 = __shfl_down_sync(0xffffffffu, sm_, off);
+      if (lane + off < 32) {
+        c += c2;
+        sm_ += s2;
+      }
+    }
+    if (lane == 0) {
+      sh.wcnt[warp] = c;
+      sh.wsum[warp] = sm_;
+    }
+    __syncthreads();
+    uint32_t hi_c = 0;
+    float hi_s = 0.f;
+    for (int w = warp + 1; w < kSelThreads / 32; ++w) {
+      hi_c += sh.wcnt[w];
+      hi_s += sh.wsum[w];
+    }
+    const uint32_t above_c = c - mycnt + hi_c;  // count in bins owned by higher threads
+    const float above_s = sm_ - mysum + hi_s;
+    if (tid == 0) {
+      sh.total = c + hi_c;
+      sh.total_sum = sm_ + hi_s;
+    }
+    if (owner && above_c < remaining && remaining <= above_c + mycnt) {
+      uint32_t run_c = above_c;
+      float run_s = above_s;
+      for (int q = per - 1; q >= 0; --q) {
+        const uint32_t h = hist[tid * per + q];
+        if (run_c + h >= remaining) {
+          sh.bsel = (uint32_t)(tid * per + q);
+          sh.above_cnt = run_c;
+          sh.above_sum = run_s;
+          sh.sel_cnt = h;
+          sh.sel_sum = sums[tid * per + q];
+          break;
+        }
+        run_c += h;
+        run_s += sums[tid * per + q];
+      }
+    }
+    __syncthreads();
+    if (sh.total < remaining) {  // fewer non-zero weights than k (only possible at the first level): keep everything
+      kept += sh.total_sum;
+      tau = 0.f;
+      break;
+    }
+    const uint32_t bsel = sh.bsel;
+    prefix |= bsel << shift;
+    pmask |= (uint32_t)(nb - 1) << shift;
+    if (pass == 2) {
+      kept += sh.above_sum + sh.sel_sum;  // every copy of the threshold value is kept
+      tau = __uint_as_float(prefix);
+      break;
+    }
+    kept += sh.above_sum;
+    remaining -= sh.above_cnt;
+    const uint32_t sel_cnt = sh.sel_cnt;
+    __syncthreads();
+    if (!use_cand && sel_cnt <= (uint32_t)kSelCap) {  // gather the survivors once; the remaining levels run from smem
+      if (tid == 0) sh.ncand = 0;
+      __syncthreads();
+      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int, float w) {
+        const uint32_t key = __float_as_uint(w);
+        if (key != 0u && (key & pmask) == prefix) cand[atomicAdd(&sh.ncand, 1)] = w;
+      });
+      __syncthreads();
+      ncand = sh.ncand;
+      use_cand = true;
+    }
+  }
+  if (tid == 0) {
+    cc[12] = tau;
+    cc[13] = tau;
+    K_NB[jb] = cj * kept;
+  }
+}
+
+// COO entries of the sparse posterior: per column the (up to) k pairs with w >= tau_j, explicit zeros filling columns
+// with fewer than k non-zero weights (the reference's sort keeps exactly k entries per column). Unordered within the
+// column; the host sorts the k values.
+__global__ void __launch_bounds__(kSelThreads)
+col_emit_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+                const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
+                const spb_scalars* __restrict__ sc, int NA, int topk, int32_t* __restrict__ rows,
+                float* __restrict__ vals) {
+  __shared__ int cnt;
+  const int jb = blockIdx.x, tid = threadIdx.x;
+  const float* cc = colconst + (int64_t)jb * 16;
+  const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10], tau = cc[12];
+  const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
+  const float* g = GT + row * ldx;
+  const float cq = sc->c_q;
+  const int k = min(topk, NA);
+  int32_t* r = rows + (int64_t)jb * topk;
+  float* v = vals + (int64_t)jb * topk;
+  if (tid == 0) cnt = 0;
+  __syncthreads();
+  sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int i, float w) {
+    if (w > tau) {
+      const int s = atomicAdd(&cnt, 1);
+      if (s < k) {
+        r[s] = i;
+        v[s] = w * cj;
+      }
+    }
+  });
+  __syncthreads();
+  // ties at the threshold (and, when tau == 0, the zero fill) until k entries exist
+  for (int i0 = 0; i0 < NA; i0 += kSelThreads * 4) {
+    if (__syncthreads_or(cnt >= k)) break;  // block-uniform: every atomic of the previous round precedes the barrier
+    const int i = i0 + tid * 4;
+    if (i < NA) {
+      const float4 G = *reinterpret_cast<const float4*>(g + i);
+      const float4 X0 = *reinterpret_cast<const float4*>(XA + i);
+      const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + i);
+      const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + i);
+      const float4 L = *reinterpret_cast<const float4*>(lm + i);
+      const float w4[4] = {pair_weight(X0.x, X1.x, X2.x, y0, y1, y2, cq, L.x, G.x),
+                           pair_weight(X0.y, X1.y, X2.y, y0, y1, y2, cq, L.y, G.y),
+                           pair_weight(X0.z, X1.z, X2.z, y0, y1, y2, cq, L.z, G.z),
+                           pair_weight(X0.w, X1.w, X2.w, y0, y1, y2, cq, L.w, G.w)};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (i + q < NA && w4[q] == tau) {
+          const int s = atomicAdd(&cnt, 1);
+          if (s < k) {
+            r[s] = i + q;
+            v[s] = w4[q] * cj;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// argmax of the posterior along both axes without materialising it (get_optimal_mapping_relationship,
+// spateo/alignment/utils.py:157-191: X_max_index = row maxima of pi, Y_max_index = column maxima)
+// ---------------------------------------------------------------------------------------------------------------------
+// key = (float bits of p) << 32 | (0xffffffff - index): unsigned max picks the largest value, lowest index on ties
+__device__ __forceinline__ unsigned long long argmax_key(float p, int idx) {
+  return ((unsigned long long)__float_as_uint(p) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)idx);
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+col_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+                  const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
+                  const spb_scalars* __restrict__ sc, int NA, unsigned long long* __restrict__ colbest) {
+  __shared__ unsigned long long red[kSelThreads / 32];
+  const int jb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* cc = colconst + (int64_t)jb * 16;
+  const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
+  const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
+  unsigned long long best = 0ull;
+  sel_for_each(GT + row * ldx, XA, ldx, lm, NA, y0, y1, y2, sc->c_q, [&](int i, float w) {
+    const unsigned long long key = argmax_key(w * cj, i);
+    best = key > best ? key : best;
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if (lane == 0) red[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kSelThreads / 32; ++w) best = red[w] > best ? red[w] : best;
+    colbest[jb] = best;
+  }
+}
+
+// one thread per moving cell, blockIdx.y = column segment; partial results are merged with a 64-bit atomicMax
+__global__ void __launch_bounds__(256)
+row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+                  const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
+                  const spb_scalars* __restrict__ sc, int NA, int NBb, unsigned long long* __restrict__ rowbest) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NA) return;
+  const int per = (NBb + gridDim.y - 1) / gridDim.y;
+  const int j0 = blockIdx.y * per, j1 = min(NBb, j0 + per);
+  const float x0 = XA[i], x1 = XA[ldx + i], x2 = XA[2 * ldx + i], li = lm[i], cq = sc->c_q;
+  unsigned long long best = 0ull;
+  for (int j = j0; j < j1; ++j) {
+    const float4 c0 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * 16);
+    const float4 c1 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * 16 + 4);
+    const float cj = colconst[(int64_t)j * 16 + 10];
+    const int64_t row = col_index ? (int64_t)col_index[j] : (int64_t)j;
+    float w = pair_weight(x0, x1, x2, c0.x, c0.z, c1.x, cq, li, GT[row * ldx + i]);
+    w = w >= colconst[(int64_t)j * 16 + 12] ? w : 0.f;  // sparse mode: entries below the column's top-k are absent
+    const unsigned long long key = argmax_key(w * cj, j);
+    best = key > best ? key : best;
+  }
+  if (j0 < j1) atomicMax(rowbest + i, best);
+}
+
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
 template <int C, int S, int B>
@@ -527,17 +843,17 @@ int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   return 0;
 }
 
-template <int C, int S, int B>
+template <int C, int S, int B, bool SP>
 int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   dim3 grid(p->ldx / kRowTile, p->seg2);
-  estep_sweep2_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
+  estep_sweep2_kernel<C, S, B, SP><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
                                                                   p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
@@ -593,11 +909,57 @@ extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
 
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
-  if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else rc = launch_sweep2<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else rc = launch_sweep2<8, 3, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   if (rc) return rc;
   SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+
+extern "C" int spb_estep_col_select(const spb_em_params* p, int32_t iter, void* stream) {
+  if (p->sparse_k <= 0) return SPB_EINVAL;
+  const size_t smem = sizeof(uint32_t) * kSelBins + sizeof(float) * kSelBins + sizeof(float) * kSelCap;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(col_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  col_select_kernel<<<p->NBb, kSelThreads, smem, (cudaStream_t)stream>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst,
+                                                                      p->XAHat, p->lm, p->sc, p->NA, p->sparse_k, p->K_NB);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_sparse_P_emit(const spb_em_params* p, int32_t iter, int32_t* rows, float* vals, void* stream) {
+  if (p->sparse_k <= 0) return SPB_EINVAL;
+  col_emit_kernel<<<p->NBb, kSelThreads, 0, (cudaStream_t)stream>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst, p->XAHat,
+                                                                    p->lm, p->sc, p->NA, p->sparse_k, rows, vals);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_posterior_argmax(const spb_em_params* p, int32_t iter, uint64_t* rowbest, uint64_t* colbest,
+                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (colbest) {
+    col_argmax_kernel<<<p->NBb, kSelThreads, 0, st>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst, p->XAHat, p->lm,
+                                                      p->sc, p->NA, (unsigned long long*)colbest);
+    SPB_CHECK_LAUNCH();
+  }
+  if (rowbest) {
+    cudaError_t e = cudaMemsetAsync(rowbest, 0, sizeof(uint64_t) * (size_t)p->NA, st);
+    if (e != cudaSuccess) return (int)e;
+    const int nrow = (p->NA + 255) / 256;
+    int nseg = (148 * 8 + nrow - 1) / nrow;
+    nseg = nseg < 1 ? 1 : (nseg > p->NBb ? p->NBb : nseg);
+    row_argmax_kernel<<<dim3(nrow, nseg), 256, 0, st>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst, p->XAHat, p->lm,
+                                                        p->sc, p->NA, p->NBb, (unsigned long long*)rowbest);
+    SPB_CHECK_LAUNCH();
+  }
   return 0;
 }
 

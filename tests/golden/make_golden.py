@@ -34,9 +34,18 @@ CASES = {
                                kw=dict(guidance_effect="both", guidance_weight=2.0), guide=True),
     "2d_svi_guide_nonrigid": dict(n_a=1250, n_b=1200, g=20, dim=2, svi=True, max_iter=110, K=15, warp=1.5,
                                   kw=dict(guidance_effect="nonrigid"), guide=True),
+    # sparse_calculation_mode (utils.py:1085-1094, morpho_class.py:1187-1198): top-k entries of every column of P
+    "2d_full_sparse48": dict(n_a=300, n_b=280, g=24, dim=2, svi=False, max_iter=110, K=15, warp=1.0,
+                             kw=dict(sparse_calculation_mode=True, sparse_top_k=48)),
+    "3d_svi_sparse32": dict(n_a=1250, n_b=1200, g=20, dim=3, svi=True, max_iter=110, K=15, warp=0.0,
+                            kw=dict(sparse_calculation_mode=True, sparse_top_k=32)),
 }
 DUMP_ITERS = (0, 3, 60, 95, 110)
 P_DUMP_ITERS = (0, 95)
+
+
+def _dense(P):
+    return P.toarray() if hasattr(P, "toarray") else P
 
 
 def run_reference(cfg, dtype, dump):
@@ -102,7 +111,7 @@ def run_reference(cfg, dtype, dump):
             e_out = dict(K_NA=ref.K_NA, K_NB=ref.K_NB, K_NA_spatial=ref.K_NA_spatial, K_NA_sigma2=ref.K_NA_sigma2,
                          sigma2_related=ref.sigma2_related, Sp=ref.Sp, Sp_spatial=ref.Sp_spatial, Sp_sigma2=ref.Sp_sigma2)
             if cfg["n_a"] <= 400 and it in P_DUMP_ITERS and dtype == "float32":
-                e_out["P"] = ref.P
+                e_out["P"] = _dense(ref.P)
             else:
                 YB = ref.coordsB[ref.batch_idx] if ref.SVI_mode else ref.coordsB
                 e_out["PXB"] = ref.P @ YB
@@ -129,12 +138,12 @@ def run_reference(cfg, dtype, dump):
     ref._wrap_output()
     for k in traj:
         out[f"traj_{k}{sfx}"] = np.array(traj[k])
-    fin = dict(P=ref.P, optimal_RnA=ref.optimal_RnA, XAHat=ref.XAHat, RnA=ref.RnA, R=ref.R, t=ref.t, Coff=ref.Coff,
+    fin = dict(P=_dense(ref.P), optimal_RnA=ref.optimal_RnA, XAHat=ref.XAHat, RnA=ref.RnA, R=ref.R, t=ref.t, Coff=ref.Coff,
                sigma2=ref.sigma2, gamma=ref.gamma, optimal_R=ref.optimal_R, optimal_t=ref.optimal_t)
     if cfg["n_a"] > 400:
         fin.pop("P")
-        fin["P_colsum"] = ref.P.sum(0)
-        fin["P_rowsum"] = ref.P.sum(1)
+        fin["P_colsum"] = np.asarray(ref.P.sum(0)).reshape(-1)
+        fin["P_rowsum"] = np.asarray(ref.P.sum(1)).reshape(-1)
     for k, v in fin.items():
         out[f"final_{k}{sfx}"] = np.asarray(v)
     return out

@@ -206,8 +206,92 @@ def test_single_estep_matches_float64_oracle(golden, case, it):
     assert abs(sc.sums[2] - P64.sum()) < 1e-5 * P64.sum()
 
 
+@pytest.mark.parametrize("it", [0, 60, 95])
+def test_sparse_estep_matches_float64_oracle(golden, it):
+    """sparse_calculation_mode (utils.py:1085-1094): the exact per-column top-k select. One E-step on the reference's
+    inputs: the emitted COO equals the top-k of the fp64 oracle's dense posterior (same support up to fp32 near-ties at
+    the k-th value, values within 1e-4), and K_NA / K_NB / P@XB are the sums of that sparse matrix."""
+    import torch
+
+    g = golden("2d_full_sparse48")
+    k = 48
+    m = _model(g, probability_parameters=[float(g["pre_beta2"])])
+    m.prepare()
+    _poke_estep_state(m, g, it)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    m._estep_only(it, st)
+    m._capture_P(it, st)
+    torch.cuda.synchronize()
+    NA, NB = m.NA, m.NB
+    P = m._sparse_P_to_coo(np.float32)
+    assert P.shape == (NA, NB) and P.nnz == k * NB
+    assert np.array_equal(P.col, np.repeat(np.arange(NB), k))
+    vals = P.data.reshape(NB, k)
+    assert (np.diff(vals, axis=1) <= 0).all()  # descending inside every column, like the reference's sort
+    for j in (0, NB // 2, NB - 1):
+        assert len(set(P.row.reshape(NB, k)[j].tolist())) == k
+    Pd = P.toarray().astype(np.float64)
+    f8 = lambda key: g[key].astype(np.float64)
+    XAHat, alpha, SD = f8(f"it{it}_in_XAHat"), f8(f"it{it}_in_alpha"), f8(f"it{it}_in_SigmaDiag")
+    sigma2, gamma = float(g[f"it{it}_in_sigma2"]), float(g[f"it{it}_in_gamma"])
+    yb = f8("pre_coordsB")
+    spatial = ((XAHat[:, None, :] - yb[None, :, :]) ** 2).sum(-1)
+    [ed] = mo.calc_distance(f8("exp_moving"), f8("exp_fixed"), "kl")
+    P64, kns, kn2, s2r = mo.get_P_core(
+        Dim=float(m.D), spatial_dist=spatial, exp_dist=[ed], sigma2=sigma2, model_mul=(alpha * np.exp(-SD / sigma2))[:, None],
+        gamma=gamma, samples_s=float(g["pre_samples_s"]), sigma2_variance=float(g[f"it{it}_in_sigma2_variance"]),
+        probability_type=["gauss"], probability_parameters=[float(g["pre_beta2"])], sparse_calculation_mode=True, top_k=k,
+    )
+    P64 = P64.toarray()
+    ref32 = g[f"it{it}_out_P"].astype(np.float64) if f"it{it}_out_P" in g else None
+    # support: identical except where the k-th and (k+1)-th largest of a column agree to fp32 rounding
+    mism = ((Pd > 0) != (P64 > 0)) & (np.maximum(Pd, P64) > 1e-30)
+    print(f"\n[sparse it{it}] support mismatches {int(mism.sum())} of {k * NB}; relF ours-vs-f64 {_relF(Pd, P64):.2e}"
+          + (f" | ref32-vs-f64 {_relF(ref32, P64):.2e}" if ref32 is not None else ""))
+    assert mism.sum() <= 2
+    ok = ~mism
+    assert np.abs(Pd - P64)[ok].max() < 1e-4 * P64.max()
+    dvec = lambda name: m._unsorted(m._state[name][:NA].cpu().numpy())
+    tol = 1e-4 if mism.sum() == 0 else 5e-3
+    assert _relmax(dvec("K_NA"), Pd.sum(1)) < 1e-5          # the sweep's sums are the sums of the emitted matrix
+    assert _relmax(m._state["K_NB"][:NB].cpu().numpy(), Pd.sum(0)) < 1e-5
+    assert _relmax(dvec("K_NA"), P64.sum(1)) < tol
+    assert _relmax(m._state["K_NB"][:NB].cpu().numpy(), P64.sum(0)) < tol
+    assert _relmax(dvec("K_NA_spatial"), kns) < 1e-4      # the other two posteriors stay dense
+    assert _relmax(dvec("K_NA_sigma2"), kn2) < 1e-4
+    pxb = m._unsorted(m._state["PXB"][: m.D, :NA].T.contiguous().cpu().numpy())
+    assert _relmax(pxb, P64 @ yb) < tol
+    # against the reference's own dump of this iteration
+    assert _relmax(dvec("K_NA"), g[f"it{it}_out_K_NA"]) < 5e-3
+    assert _relmax(m._state["K_NB"][:NB].cpu().numpy(), g[f"it{it}_out_K_NB"]) < 5e-3
+
+
+def test_sparse_mode_edge_cases():
+    """top_k larger than N_A keeps everything (utils.py:1387-1388) and equals the dense run; top_k = 1 keeps the argmax."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(700, 650, 30, dim=2, seed=3)
+    kw = dict(SVI_mode=False, max_iter=40, nonrigid_start_iter=20, verbose=False, device="0")
+    np.random.seed(0)
+    dense = st.align.Morpho_pairwise(sampleA=B, sampleB=A, **kw)
+    Pd = dense.run()
+    np.random.seed(0)
+    big = st.align.Morpho_pairwise(sampleA=B, sampleB=A, sparse_calculation_mode=True, sparse_top_k=5000, **kw)
+    Pb = big.run()
+    assert Pb.nnz == Pd.shape[0] * Pd.shape[1]
+    assert np.abs(big.optimal_RnA - dense.optimal_RnA).max() < 1e-4 * np.abs(dense.optimal_RnA).max()
+    assert _relF(Pb.toarray(), Pd) < 1e-4
+    np.random.seed(0)
+    one = st.align.Morpho_pairwise(sampleA=B, sampleB=A, sparse_calculation_mode=True, sparse_top_k=1, **kw)
+    P1 = one.run()
+    assert P1.nnz == Pd.shape[1] and np.isfinite(one.optimal_RnA).all()
+    with pytest.raises(ValueError):
+        st.align.Morpho_pairwise(sampleA=B, sampleB=A, sparse_calculation_mode=True, sparse_top_k=0, **kw)
+
+
 @pytest.mark.parametrize("case", ["2d_full", "3d_full_warp", "2d_full_nonn_euc", "3d_svi", "2d_full_guide_both",
-                                  "2d_svi_guide_nonrigid"])
+                                  "2d_svi_guide_nonrigid", "2d_full_sparse48", "3d_svi_sparse32"])
 def test_full_run_matches_reference(golden, case):
     """Whole alignment through the public class: aligned coordinates within 1e-3 (relative to the coordinate range)
     of BOTH the float32 and the float64 reference runs; sigma2 / gamma close; P against the float64 reference."""
@@ -230,6 +314,10 @@ def test_full_run_matches_reference(golden, case):
     assert _relmax(m.optimal_R, g["final_optimal_R"]) < 1e-3
     assert _relmax(m.optimal_R, g["final_optimal_R_f64"]) < max(
         1e-3, 2 * _relmax(g["final_optimal_R"], g["final_optimal_R_f64"]))
+    if hasattr(P, "toarray"):  # sparse_calculation_mode: scipy COO with top_k entries per column
+        k = _cfg(g)["kw"]["sparse_top_k"]
+        assert P.nnz == k * P.shape[1] and P.dtype == np.float32
+        P = P.toarray()
     if "final_P_f64" in g:
         ours = _relF(P, g["final_P_f64"])
         theirs = _relF(g["final_P"], g["final_P_f64"])

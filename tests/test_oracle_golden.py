@@ -8,11 +8,17 @@ import pytest
 
 from oracle import morpho_oracle as mo
 
-CASES = ["2d_full", "3d_svi", "3d_full_warp", "2d_full_nonn_euc", "2d_full_guide_both", "2d_svi_guide_nonrigid"]
+CASES = ["2d_full", "3d_svi", "3d_full_warp", "2d_full_nonn_euc", "2d_full_guide_both", "2d_svi_guide_nonrigid",
+         "2d_full_sparse48", "3d_svi_sparse32"]
 
 
 def _cfg(g):
     return ast.literal_eval(str(g["cfg"]))
+
+
+def cfg_sparse(g):
+    kw = _cfg(g)["kw"]
+    return kw.get("sparse_top_k", 1024) if kw.get("sparse_calculation_mode") else 0
 
 
 def _relmax(a, b):
@@ -93,7 +99,10 @@ def test_full_run_matches_reference(golden, case, dtype):
     assert _relmax(orc.gamma, g["final_gamma" + sfx]) < 1e-3
     assert _relmax(orc.optimal_R, g["final_optimal_R" + sfx]) < tol
     if "final_P" + sfx in g:
-        num = np.linalg.norm(orc.P.astype(np.float64) - g["final_P" + sfx])
+        P = orc.P.toarray() if hasattr(orc.P, "toarray") else orc.P
+        if cfg_sparse(g):
+            assert (P > 0).sum(0).max() <= cfg_sparse(g)  # at most top_k stored entries per column
+        num = np.linalg.norm(P.astype(np.float64) - g["final_P" + sfx])
         assert num / np.linalg.norm(g["final_P" + sfx]) < (2e-2 if dtype == "float32" else 1e-5)
 
 
