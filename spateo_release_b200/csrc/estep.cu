@@ -144,6 +144,119 @@ __device__ __forceinline__ void butterfly_reduce(float (&acc)[NV], int lane) {
   bfly_step<NV / 32, 1, NV>(acc, lane);
 }
 
+// ---- per-thread state and per-stage math shared by the two-kernel path and the fused persistent kernel --------------
+struct RowRegs {  // 4 consecutive moving cells as two packed pairs (a = rows r, r+1; b = rows r+2, r+3)
+  u64 xa0, xb0, xa1, xb1, xa2, xb2, lma, lmb, mma, mmb;
+};
+__device__ __forceinline__ RowRegs load_rows(const float* __restrict__ XA, int64_t ldx, const float* __restrict__ lm,
+                                             const float* __restrict__ mm, int r) {
+  const float4 X0 = *reinterpret_cast<const float4*>(XA + r);
+  const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + r);
+  const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + r);
+  const float4 LM = *reinterpret_cast<const float4*>(lm + r);
+  RowRegs R;
+  R.xa0 = pk(X0.x, X0.y), R.xb0 = pk(X0.z, X0.w), R.xa1 = pk(X1.x, X1.y), R.xb1 = pk(X1.z, X1.w);
+  R.xa2 = pk(X2.x, X2.y), R.xb2 = pk(X2.z, X2.w);
+  R.lma = pk(LM.x, LM.y), R.lmb = pk(LM.z, LM.w);
+  if (mm) {
+    const float4 MM = *reinterpret_cast<const float4*>(mm + r);
+    R.mma = pk(MM.x, MM.y), R.mmb = pk(MM.z, MM.w);
+  } else {
+    R.mma = R.mmb = 0ull;
+  }
+  return R;
+}
+
+// sweep 1, one pipeline stage: per column the four partial sums of this thread's 4 rows (index v * kColStage + jj)
+template <int kColStage, int kStages>
+__device__ __forceinline__ void sweep1_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
+                                             u64 CQ, u64 CS, float (&acc)[4 * kColStage]) {
+#pragma unroll
+  for (int jj = 0; jj < kColStage; ++jj) {
+    const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
+    const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (0,0)
+    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+    const u64 da = sqdist2(R.xa0, R.xa1, R.xa2, ya.x, ya.y, yb.x);
+    const u64 db = sqdist2(R.xb0, R.xb1, R.xb2, ya.x, ya.y, yb.x);
+    const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+    const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
+    acc[0 * kColStage + jj] = hsum(add2(sa, sb));
+    acc[1 * kColStage + jj] = hsum(fma2(sa, R.mma, mul2(sb, R.mmb)));
+    acc[2 * kColStage + jj] = hsum(add2(qa, qb));
+    acc[3 * kColStage + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
+  }
+}
+
+// sweep 2 accumulators: [row pair a | b] x {K_NA_spatial/m, K_NA_sigma2, sum Psigma d, K_NA, (P@XB)_x, _y, _z}
+struct S2Acc {
+  u64 spa, spb, s2a, s2b, sda, sdb, ka, kb, pxa, pxb, pya, pyb, pza, pzb;
+  __device__ __forceinline__ void clear() {
+    const u64 Z = pk(0.f, 0.f);
+    spa = spb = s2a = s2b = sda = sdb = ka = kb = pxa = pxb = pya = pyb = pza = pzb = Z;
+  }
+  __device__ __forceinline__ void store(float* __restrict__ out, int64_t ldx) const {
+    auto st4 = [&](int q, u64 a, u64 b) {
+      float4 v;
+      upk(a, v.x, v.y);
+      upk(b, v.z, v.w);
+      *reinterpret_cast<float4*>(out + (int64_t)q * ldx) = v;
+    };
+    st4(0, spa, spb);
+    st4(1, s2a, s2b);
+    st4(2, sda, sdb);
+    st4(3, ka, kb);
+    st4(4, pxa, pxb);
+    st4(5, pya, pyb);
+    st4(6, pza, pzb);
+  }
+};
+
+// kSparse (sparse_calculation_mode, utils.py:1085-1094): only pairs whose weight q g reaches the column's top-k threshold
+// tau_j (col_select_kernel) enter K_NA and P @ XB; the spatial and sigma2 posteriors stay dense as in the reference.
+__device__ __forceinline__ u64 keep_ge(u64 w, float tau) {
+  float a, b;
+  upk(w, a, b);
+  return pk(a >= tau ? a : 0.f, b >= tau ? b : 0.f);
+}
+
+template <int kColStage, int kStages, bool kSparse>
+__device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
+                                             u64 CQ, u64 CS, S2Acc& A) {
+#pragma unroll
+  for (int jj = 0; jj < kColStage; ++jj) {
+    const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
+    const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
+    const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
+    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+    const u64 da = sqdist2(R.xa0, R.xa1, R.xa2, c0.x, c0.y, c1.x);
+    const u64 db = sqdist2(R.xb0, R.xb1, R.xb2, c0.x, c0.y, c1.x);
+    const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+    const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
+    A.spa = fma2(sa, c1.y, A.spa);
+    A.spb = fma2(sb, c1.y, A.spb);
+    const u64 ta = mul2(qa, c2.x), tb = mul2(qb, c2.x);
+    A.s2a = add2(A.s2a, ta);
+    A.s2b = add2(A.s2b, tb);
+    A.sda = fma2(ta, da, A.sda);
+    A.sdb = fma2(tb, db, A.sdb);
+    u64 wa = mul2(qa, g.x), wb = mul2(qb, g.y);
+    if constexpr (kSparse) {
+      const float tau = sm.cols[s][jj][3].x;
+      wa = keep_ge(wa, tau);
+      wb = keep_ge(wb, tau);
+    }
+    const u64 pa = mul2(wa, c2.y), pb = mul2(wb, c2.y);
+    A.ka = add2(A.ka, pa);
+    A.kb = add2(A.kb, pb);
+    A.pxa = fma2(pa, c0.x, A.pxa);
+    A.pxb = fma2(pb, c0.x, A.pxb);
+    A.pya = fma2(pa, c0.y, A.pya);
+    A.pyb = fma2(pb, c0.y, A.pyb);
+    A.pza = fma2(pa, c1.x, A.pza);
+    A.pzb = fma2(pb, c1.x, A.pzb);
+  }
+}
+
 __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const float4& y) {
   const float d0 = x0 - y.x, d1 = x1 - y.y, d2 = x2 - y.z;
   return fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
@@ -182,15 +295,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   }
   // ---- consumers: 4 rows per thread = 2 packed row pairs ----
   const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
-  const int r = i0 + tid * 4;
-  const float4 X0 = *reinterpret_cast<const float4*>(XA + r);
-  const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + r);
-  const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + r);
-  const float4 LM = *reinterpret_cast<const float4*>(lm + r);
-  const float4 MM = *reinterpret_cast<const float4*>(mm + r);
-  const u64 xa0 = pk(X0.x, X0.y), xb0 = pk(X0.z, X0.w), xa1 = pk(X1.x, X1.y), xb1 = pk(X1.z, X1.w);
-  const u64 xa2 = pk(X2.x, X2.y), xb2 = pk(X2.z, X2.w);
-  const u64 lma = pk(LM.x, LM.y), lmb = pk(LM.z, LM.w), mma = pk(MM.x, MM.y), mmb = pk(MM.z, MM.w);
+  const RowRegs R = load_rows(XA, ldx, lm, mm, i0 + tid * 4);
   const int nst = (cr.end - cr.begin + kColStage - 1) / kColStage;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
@@ -198,20 +303,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     const int pb = cr.begin + st * kColStage;
     constexpr int NV = 4 * kColStage;  // partial sums per thread per stage, index v * kColStage + jj
     float acc[NV];
-#pragma unroll
-    for (int jj = 0; jj < kColStage; ++jj) {
-      const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
-      const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (0,0)
-      const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
-      const u64 da = sqdist2(xa0, xa1, xa2, ya.x, ya.y, yb.x);
-      const u64 db = sqdist2(xb0, xb1, xb2, ya.x, ya.y, yb.x);
-      const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
-      const u64 qa = ex2_2(fma2(CQ, da, lma)), qb = ex2_2(fma2(CQ, db, lmb));
-      acc[0 * kColStage + jj] = hsum(add2(sa, sb));
-      acc[1 * kColStage + jj] = hsum(fma2(sa, mma, mul2(sb, mmb)));
-      acc[2 * kColStage + jj] = hsum(add2(qa, qb));
-      acc[3 * kColStage + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
-    }
+    sweep1_stage<kColStage, kStages>(sm, s, tid, R, CQ, CS, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // stage buffer is free again
     butterfly_reduce<NV>(acc, lane);
@@ -261,14 +353,6 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 2: row statistics
 // ---------------------------------------------------------------------------------------------------------------------
-// kSparse (sparse_calculation_mode, utils.py:1085-1094): only pairs whose weight q g reaches the column's top-k threshold
-// tau_j (col_select_kernel) enter K_NA and P @ XB; the spatial and sigma2 posteriors stay dense as in the reference.
-__device__ __forceinline__ u64 keep_ge(u64 w, float tau) {
-  float a, b;
-  upk(w, a, b);
-  return pk(a >= tau ? a : 0.f, b >= tau ? b : 0.f);
-}
-
 template <int kColStage, int kStages, int kMinBlocks, bool kSparse>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
@@ -298,70 +382,18 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   }
   const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
   const int r = i0 + tid * 4;
-  const float4 X0 = *reinterpret_cast<const float4*>(XA + r);
-  const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + r);
-  const float4 X2 = *reinterpret_cast<const float4*>(XA + 2 * ldx + r);
-  const float4 LM = *reinterpret_cast<const float4*>(lm + r);
-  const u64 xa0 = pk(X0.x, X0.y), xb0 = pk(X0.z, X0.w), xa1 = pk(X1.x, X1.y), xb1 = pk(X1.z, X1.w);
-  const u64 xa2 = pk(X2.x, X2.y), xb2 = pk(X2.z, X2.w);
-  const u64 lma = pk(LM.x, LM.y), lmb = pk(LM.z, LM.w);
-  const u64 Z = pk(0.f, 0.f);
-  // accumulators: [row pair a | b] x {K_NA_spatial/m, K_NA_sigma2, sum Psigma d, K_NA, (P@XB)_x, _y, _z}
-  u64 spa = Z, spb = Z, s2a = Z, s2b = Z, sda = Z, sdb = Z, ka = Z, kb = Z, pxa = Z, pxb = Z, pya = Z, pyb = Z, pza = Z, pzb = Z;
+  const RowRegs R = load_rows(XA, ldx, lm, nullptr, r);
+  S2Acc A;
+  A.clear();
   const int nst = j_begin < j_end ? (j_end - j_begin + kColStage - 1) / kColStage : 0;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
     mbar_wait(&sm.full[s], (st / kStages) & 1);
-#pragma unroll
-    for (int jj = 0; jj < kColStage; ++jj) {
-      const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
-      const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
-      const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
-      const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
-      const u64 da = sqdist2(xa0, xa1, xa2, c0.x, c0.y, c1.x);
-      const u64 db = sqdist2(xb0, xb1, xb2, c0.x, c0.y, c1.x);
-      const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
-      const u64 qa = ex2_2(fma2(CQ, da, lma)), qb = ex2_2(fma2(CQ, db, lmb));
-      spa = fma2(sa, c1.y, spa);
-      spb = fma2(sb, c1.y, spb);
-      const u64 ta = mul2(qa, c2.x), tb = mul2(qb, c2.x);
-      s2a = add2(s2a, ta);
-      s2b = add2(s2b, tb);
-      sda = fma2(ta, da, sda);
-      sdb = fma2(tb, db, sdb);
-      u64 wa = mul2(qa, g.x), wb = mul2(qb, g.y);
-      if constexpr (kSparse) {
-        const float tau = sm.cols[s][jj][3].x;
-        wa = keep_ge(wa, tau);
-        wb = keep_ge(wb, tau);
-      }
-      const u64 pa = mul2(wa, c2.y), pb = mul2(wb, c2.y);
-      ka = add2(ka, pa);
-      kb = add2(kb, pb);
-      pxa = fma2(pa, c0.x, pxa);
-      pxb = fma2(pb, c0.x, pxb);
-      pya = fma2(pa, c0.y, pya);
-      pyb = fma2(pb, c0.y, pyb);
-      pza = fma2(pa, c1.x, pza);
-      pzb = fma2(pb, c1.x, pzb);
-    }
+    sweep2_stage<kColStage, kStages, kSparse>(sm, s, tid, R, CQ, CS, A);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);
   }
-  float* out = rowpart + ((int64_t)seg * 8) * ldx + r;
-  auto st4 = [&](int q, u64 a, u64 b) {
-    float4 v;
-    upk(a, v.x, v.y);
-    upk(b, v.z, v.w);
-    *reinterpret_cast<float4*>(out + (int64_t)q * ldx) = v;
-  };
-  st4(0, spa, spb);
-  st4(1, s2a, s2b);
-  st4(2, sda, sdb);
-  st4(3, ka, kb);
-  st4(4, pxa, pxb);
-  st4(5, pya, pyb);
-  st4(6, pza, pzb);
+  A.store(rowpart + ((int64_t)seg * 8) * ldx + r, ldx);
 }
 
 // per row: fold the segment partials (fp64), write the fp32 statistics, accumulate the global sums
@@ -524,6 +556,235 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused persistent E-step: sweep 1, the column constants and sweep 2 in ONE cooperative launch, ordered so that the second
+// read of every GT element comes from L2 instead of HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+// The columns of the iteration are cut into panels of W = nseg * cpp columns (tens of MB of GT, a fraction of the 126 MB
+// L2). CTA (rb, seg) owns row block rb for the whole launch and, in panel p, the seg-th slice of its block's column list
+// inside the panel. Step t of every CTA: phase A(t) = sweep-1 partial column sums of panel t; then phase B(t-1) =
+// sweep-2 row statistics of panel t-1, whose GT rows were streamed one step earlier and are still L2-resident.
+// Between the two, the LAST CTA to finish A(t) (atomic ticket) turns the partial sums of panel t into the column
+// constants (same fp64 fixed-order sum as col_finalize_kernel) and publishes ready[t]; nobody ever waits for work that
+// was not already finished a whole step ago, so the flag latency is hidden. Results are bit-identical to the two-kernel
+// path: same per-thread arithmetic, same column order per CTA, same reduction trees.
+// HBM traffic: 4 B per cell pair per iteration (algorithmic: 8 B); the second 4 B are L2 hits.
+struct FusedArgs {
+  const float* GT;
+  int64_t ldx;
+  const int32_t* col_index;
+  const float* colgeom;
+  float* colconst;
+  const float* XA;
+  const float* lm;
+  const float* mm;
+  const spb_scalars* sc;
+  float* colpart;
+  float* rowpart;
+  float* K_NB;
+  int NBb, nbb_pad, nrb, W, NP;
+  const int32_t* collist;
+  const int32_t* panel_off;  // [nrb][NP + 1] position of the first list entry >= p * W
+  int32_t* flags;            // [2][NP]: tickets of finished A phases, ready flags (zeroed before the launch)
+  int l2_hints;              // 1: phase A loads GT evict_last, phase B evict_first
+};
+
+__device__ __forceinline__ int ld_acquire(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// slice of panel t owned by this CTA: list positions [b, e)
+__device__ __forceinline__ void fused_range(const int32_t* __restrict__ poff, int t, int seg, int nseg, int& b, int& e) {
+  const int lo = poff[t], hi = poff[t + 1];
+  int per = (hi - lo + nseg - 1) / nseg;
+  per = ((per + 7) / 8) * 8;
+  b = min(hi, lo + seg * per);
+  e = min(hi, b + per);
+}
+
+template <int kColStage, int kStages>
+__global__ void __launch_bounds__(kThreads, 2) estep_fused_kernel(const FusedArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  using Smem = SmemLayoutT<kColStage, kStages>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
+  const int ncta = gridDim.x * gridDim.y;
+  const int i0 = rb * kRowTile;
+  const int32_t* list = a.collist + (int64_t)rb * a.nbb_pad;
+  const int32_t* poff = a.panel_off + (int64_t)rb * (a.NP + 1);
+  int32_t* ticket = a.flags;
+  int32_t* ready = a.flags + a.NP;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sm.full[s], 1);
+      mbar_init(&sm.empty[s], kConsumers / 32);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == kConsumers / 32) {
+    // ---- producer warp: one continuous ring over all phases ----
+    int gst = 0;
+    const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
+    auto issue = [&](int b, int e, const float* colsrc, int col_floats, int hint) {
+      const int nst = (e - b + kColStage - 1) / kColStage;
+      for (int st = 0; st < nst; ++st, ++gst) {
+        const int s = gst % kStages;
+        if (gst >= kStages) mbar_wait(&sm.empty[s], ((gst / kStages) - 1) & 1);
+        const int pb = b + st * kColStage;
+        if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)(kColStage * kRowTile * 4 + kColStage * col_floats * 4));
+        __syncwarp();
+        if (lane < kColStage) {
+          const bool live = pb + lane < e;
+          const int j = live ? list[pb + lane] : a.NBb;
+          const int jr = live ? j : list[e - 1];
+          const int64_t row = a.col_index ? (int64_t)a.col_index[jr] : (int64_t)jr;
+          if (hint == 0) bulk_g2s(&sm.tile[s][lane][0], a.GT + row * a.ldx + i0, kRowTile * 4, &sm.full[s]);
+          else bulk_g2s_hint(&sm.tile[s][lane][0], a.GT + row * a.ldx + i0, kRowTile * 4, &sm.full[s], hint == 1 ? pol_a : pol_b);
+          bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)j * col_floats, col_floats * 4, &sm.full[s]);
+        }
+      }
+    };
+    for (int t = 0; t <= a.NP; ++t) {
+      int b, e;
+      if (t < a.NP) {
+        fused_range(poff, t, seg, nseg, b, e);
+        issue(b, e, a.colgeom, 8, a.l2_hints ? 1 : 0);
+      }
+      if (t >= 1) {
+        fused_range(poff, t - 1, seg, nseg, b, e);
+        if (b < e) {
+          if (lane == 0) {
+            while (ld_acquire(ready + (t - 1)) == 0) __nanosleep(64);
+          }
+          __syncwarp();
+          asm volatile("fence.proxy.async.global;" ::: "memory");  // constants were written through the generic proxy
+          issue(b, e, a.colconst, 16, a.l2_hints ? 2 : 0);
+        }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const u64 CQ = pk(a.sc->c_q, a.sc->c_q), CS = pk(a.sc->c_s, a.sc->c_s);
+  const int r = i0 + tid * 4;
+  const RowRegs R = load_rows(a.XA, a.ldx, a.lm, a.mm, r);
+  S2Acc A;
+  A.clear();
+  int gst = 0, ast = 0;
+  for (int t = 0; t <= a.NP; ++t) {
+    int b, e;
+    if (t < a.NP) {
+      // ---------------- phase A(t): partial column sums ----------------
+      fused_range(poff, t, seg, nseg, b, e);
+      const int nst = (e - b + kColStage - 1) / kColStage;
+      for (int st = 0; st < nst; ++st, ++gst, ++ast) {
+        const int s = gst % kStages;
+        mbar_wait(&sm.full[s], (gst / kStages) & 1);
+        const int pb = b + st * kColStage;
+        constexpr int NV = 4 * kColStage;
+        float acc[NV];
+        sweep1_stage<kColStage, kStages>(sm, s, tid, R, CQ, CS, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        butterfly_reduce<NV>(acc, lane);
+        constexpr int kShift = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
+        const int buf = ast & 1;
+        if ((lane & ((1 << kShift) - 1)) == 0) sm.red[buf][warp][lane >> kShift] = acc[0];
+        named_bar_sync(1, kConsumers);
+        if (warp == 0 && lane < NV) {
+          float tsum = 0.f;
+#pragma unroll
+          for (int w = 0; w < kConsumers / 32; ++w) tsum += sm.red[buf][w][lane];
+          const int v = lane / kColStage, jj = lane % kColStage;
+          if (pb + jj < e) a.colpart[((int64_t)rb * 4 + v) * a.nbb_pad + list[pb + jj]] = tsum;
+        }
+      }
+      // ticket: the last CTA to finish A(t) owns the column constants of panel t
+      if (warp == 0) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) s_last = (atomicAdd(ticket + t, 1) == ncta - 1);
+      }
+      named_bar_sync(1, kConsumers);
+      if (s_last) {
+        __threadfence();
+        const int j0 = t * a.W, j1 = min(a.NBb, j0 + a.W);
+        const double omega = a.sc->omega;
+        for (int j = j0 + (tid >> 1); j < j1; j += kConsumers / 2) {
+          // two threads per column: even lane sums C0, C1, odd lane C2, C3 (fp64, row blocks in order)
+          const int h = tid & 1;
+          double c0 = 0.0, c1 = 0.0;
+          for (int q = 0; q < a.nrb; ++q) {
+            c0 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h) * a.nbb_pad + j);
+            c1 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h + 1) * a.nbb_pad + j);
+          }
+          const double o0 = __shfl_xor_sync(0xffffffffu, c0, 1), o1 = __shfl_xor_sync(0xffffffffu, c1, 1);
+          if (h == 0) {
+            const double C0 = c0, C1 = c1, C2 = o0, C3 = o1;
+            const double inl = 1.0 - omega / (omega + C0);
+            const double ca = 1.0 / (omega + C1);
+            const double cb = inl / (C2 + 1e-8);
+            const double cc = inl / (C3 + 1e-8);
+            const float* yg = a.colgeom + (int64_t)j * 8;
+            const float y0 = yg[0], y1 = yg[2], y2 = yg[4];
+            const float af = (float)ca, bf = (float)cb, cf = (float)cc;
+            float4* out = reinterpret_cast<float4*>(a.colconst + (int64_t)j * 16);
+            out[0] = make_float4(y0, y0, y1, y1);
+            out[1] = make_float4(y2, y2, af, af);
+            out[2] = make_float4(bf, bf, cf, cf);
+            out[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a.K_NB[j] = (float)(cc * C3);
+          }
+        }
+        __threadfence();
+        named_bar_sync(1, kConsumers);
+        if (tid == 0) st_release(ready + t, 1);
+      }
+    }
+    if (t >= 1) {
+      // ---------------- phase B(t-1): row statistics, GT panel read back from L2 ----------------
+      fused_range(poff, t - 1, seg, nseg, b, e);
+      const int nst = (e - b + kColStage - 1) / kColStage;
+      for (int st = 0; st < nst; ++st, ++gst) {
+        const int s = gst % kStages;
+        mbar_wait(&sm.full[s], (gst / kStages) & 1);
+        sweep2_stage<kColStage, kStages, false>(sm, s, tid, R, CQ, CS, A);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+      }
+    }
+  }
+  A.store(a.rowpart + ((int64_t)seg * 8) * a.ldx + r, a.ldx);
+}
+
+// panel_off[rb][p] = number of entries of row block rb's column list that are < p * W (p = 0..NP)
+__global__ void panel_offsets_kernel(const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount, int nbb_pad,
+                                     int W, int NP, int32_t* __restrict__ panel_off) {
+  const int rb = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > NP) return;
+  const int32_t* list = collist + (int64_t)rb * nbb_pad;
+  const int n = colcount[rb];
+  const int key = p * W;
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (list[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  panel_off[(int64_t)rb * (NP + 1) + p] = lo;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // sparse_calculation_mode: per-column top-k of the full posterior (utils.py:1085-1094 -> _dense_to_sparse :1369-1404)
@@ -826,6 +1087,7 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   if (j0 < j1) atomicMax(rowbest + i, best);
 }
 
+int g_fuse_l2_hints = 0;  // spb_set_sweep_config(10 + h) sets it
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
 template <int C, int S, int B>
@@ -871,6 +1133,10 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
 }
 
 extern "C" int spb_set_sweep_config(int32_t cfg) {
+  if (cfg == 10 || cfg == 11) {  // L2 eviction hints of the fused E-step off / on
+    g_fuse_l2_hints = cfg - 10;
+    return 0;
+  }
   if (cfg < 0 || cfg > 2) return SPB_EINVAL;
   g_sweep_cfg = cfg;
   return 0;
@@ -960,6 +1226,47 @@ extern "C" int spb_posterior_argmax(const spb_em_params* p, int32_t iter, uint64
                                                         p->sc, p->NA, p->NBb, (unsigned long long*)rowbest);
     SPB_CHECK_LAUNCH();
   }
+  return 0;
+}
+
+// Fused persistent E-step (estep_fused_kernel): replaces spb_estep_sweep1 + spb_col_finalize + spb_estep_sweep2.
+// Needs p->fuse_W > 0 (panel width, a multiple of 8 * fuse_nseg), p->panel_off, p->fuse_flags, dense mode, and
+// (ldx / ROW_TILE) * fuse_nseg co-resident CTAs; returns SPB_EUNSUPPORTED otherwise (the caller then uses the 3 kernels).
+extern "C" int spb_estep_fused(const spb_em_params* p, int32_t iter, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->fuse_W <= 0 || p->fuse_nseg <= 0 || p->sparse_k > 0 || !p->panel_off || !p->fuse_flags) return SPB_EUNSUPPORTED;
+  using Smem = SmemLayoutT<8, 3>;
+  static int max_ctas = -1;
+  if (max_ctas < 0) {
+    cudaError_t e = cudaFuncSetAttribute(estep_fused_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_fused_kernel<8, 3>, kThreads, sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    max_ctas = sms * per_sm;
+  }
+  const int nrb = p->ldx / kRowTile;
+  if (nrb * p->fuse_nseg > max_ctas) return SPB_EUNSUPPORTED;
+  const int NP = (p->NBb + p->fuse_W - 1) / p->fuse_W;
+  cudaError_t e = cudaMemsetAsync(p->colpart, 0, sizeof(float) * (size_t)nrb * 4 * p->nbb_pad, st);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(p->fuse_flags, 0, sizeof(int32_t) * 2 * (size_t)NP, st);
+  if (e != cudaSuccess) return (int)e;
+  panel_offsets_kernel<<<dim3((NP + 1 + 127) / 128, nrb), 128, 0, st>>>(p->collist, p->colcount, p->nbb_pad, p->fuse_W, NP,
+                                                                      p->panel_off);
+  SPB_CHECK_LAUNCH();
+  FusedArgs a;
+  a.GT = p->GT; a.ldx = p->ldx; a.col_index = batch_ptr(p, iter); a.colgeom = p->colgeom; a.colconst = p->colconst;
+  a.XA = p->XAHat; a.lm = p->lm; a.mm = p->mm; a.sc = p->sc; a.colpart = p->colpart; a.rowpart = p->rowpart;
+  a.K_NB = p->K_NB; a.NBb = p->NBb; a.nbb_pad = p->nbb_pad; a.nrb = nrb; a.W = p->fuse_W; a.NP = NP;
+  a.collist = p->collist; a.panel_off = p->panel_off; a.flags = p->fuse_flags; a.l2_hints = g_fuse_l2_hints;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)estep_fused_kernel<8, 3>, dim3(nrb, p->fuse_nseg), dim3(kThreads), args,
+                                  sizeof(Smem), st);
+  if (e != cudaSuccess) return (int)e;
+  SPB_CHECK_LAUNCH();
   return 0;
 }
 
