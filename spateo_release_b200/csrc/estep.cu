@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 2) estep_fused_kernel(const FusedArg
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using Smem = SmemLayoutT<kColStage, kStages>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  __shared__ int s_last;
+  __shared__ int s_last[2];  // double-buffered by step parity: a fast warp may reach the next ticket early
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
   const int ncta = gridDim.x * gridDim.y;
@@ -664,7 +664,13 @@ __global__ void __launch_bounds__(kThreads, 2) estep_fused_kernel(const FusedArg
         fused_range(poff, t - 1, seg, nseg, b, e);
         if (b < e) {
           if (lane == 0) {
-            while (ld_acquire(ready + (t - 1)) == 0) __nanosleep(64);
+            unsigned long long t0 = 0, now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            while (ld_acquire(ready + (t - 1)) == 0) {
+              __nanosleep(64);
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (now - t0 > 4000000000ull) __trap();  // 4 s without progress: abort the launch instead of hanging
+            }
           }
           __syncwarp();
           asm volatile("fence.proxy.async.global;" ::: "memory");  // constants were written through the generic proxy
@@ -714,23 +720,27 @@ __global__ void __launch_bounds__(kThreads, 2) estep_fused_kernel(const FusedArg
       if (warp == 0) {
         __threadfence();
         __syncwarp();
-        if (lane == 0) s_last = (atomicAdd(ticket + t, 1) == ncta - 1);
+        if (lane == 0) s_last[t & 1] = (atomicAdd(ticket + t, 1) == ncta - 1);
       }
       named_bar_sync(1, kConsumers);
-      if (s_last) {
+      if (s_last[t & 1]) {
         __threadfence();
         const int j0 = t * a.W, j1 = min(a.NBb, j0 + a.W);
         const double omega = a.sc->omega;
-        for (int j = j0 + (tid >> 1); j < j1; j += kConsumers / 2) {
+        for (int jb = j0; jb < j1; jb += kConsumers / 2) {  // warp-uniform trip count: the shuffles below need all lanes
           // two threads per column: even lane sums C0, C1, odd lane C2, C3 (fp64, row blocks in order)
+          const int j = jb + (tid >> 1);
+          const bool ok = j < j1;
           const int h = tid & 1;
           double c0 = 0.0, c1 = 0.0;
-          for (int q = 0; q < a.nrb; ++q) {
-            c0 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h) * a.nbb_pad + j);
-            c1 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h + 1) * a.nbb_pad + j);
+          if (ok) {
+            for (int q = 0; q < a.nrb; ++q) {
+              c0 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h) * a.nbb_pad + j);
+              c1 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h + 1) * a.nbb_pad + j);
+            }
           }
           const double o0 = __shfl_xor_sync(0xffffffffu, c0, 1), o1 = __shfl_xor_sync(0xffffffffu, c1, 1);
-          if (h == 0) {
+          if (ok && h == 0) {
             const double C0 = c0, C1 = c1, C2 = o0, C3 = o1;
             const double inl = 1.0 - omega / (omega + C0);
             const double ca = 1.0 / (omega + C1);
