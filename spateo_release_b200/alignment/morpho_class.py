@@ -283,7 +283,7 @@ class Morpho_pairwise:
         self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
         if fuse_estep is None:
-            fuse_estep = os.environ.get("SPB_FUSE_ESTEP", "1") != "0"
+            fuse_estep = os.environ.get("SPB_FUSE_ESTEP", "0") == "1"  # experimental, see DESIGN.md (slower today)
         self.fuse_estep = bool(fuse_estep)
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64

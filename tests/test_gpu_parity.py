@@ -659,6 +659,6 @@ def test_fused_estep_equals_three_kernel_path(svi, cull, monkeypatch):
         assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item(), k
     sf, su = mf._read_scalars(), mu._read_scalars()
     for q in range(4):
-        assert abs(sf.sums[q] - su.sums[q]) <= 1e-9 * abs(su.sums[q])
+        assert abs(sf.sums[q] - su.sums[q]) <= 1e-7 * abs(su.sums[q])  # fp32 partials of a different segment split
     # and the trajectories of the two complete 25-iteration runs agree
     assert np.abs(tf - tu).max() <= 1e-5 * np.abs(tu).max()
