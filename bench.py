@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--cpu-cells", type=int, default=6000, help="cells per slice of the bounded CPU-baseline sample")
     ap.add_argument("--cpu-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary EM-loop timings (default SVI mode; K=200 inducing points) of SURVEY.md 8(d) config 2")
     ap.add_argument("--workload", default="pair", choices=["pair", "vfc"],
                     help="pair = BASELINE configs[1] (headline); vfc = configs[4] SparseVFC (secondary line)")
     ap.add_argument("--vfc-cells", type=int, default=1000000)
@@ -440,6 +442,38 @@ def main():
         },
     }
 
+    # ---- secondary configurations of config 2: default SVI mode and K = 200, EM loop only, 1 step each ----
+    secondary = None
+    if world == 1 and not args.no_secondary and not args.svi:
+        secondary = {}
+        sig_final, gam_final = float(m.sigma2), float(m.gamma)
+        m.__dict__.pop("_GT", None)
+        m.__dict__.pop("_state", None)
+        torch.cuda.empty_cache()
+        for tag, kw in (("svi_default_batch", dict(SVI_mode=True, K=args.K)), ("full_em_K200", dict(SVI_mode=False, K=200))):
+            np.random.seed(rank)
+            m2 = st.align.Morpho_pairwise(sampleA=B, sampleB=A, max_iter=args.max_iter, nn_init=True, verbose=False,
+                                          device=str(local_rank), materialize_P=False, **kw)
+            m2.prepare()
+            cols2 = m2.batch_size if m2.SVI_mode else NB
+            ms2 = []
+            for srep in range(2):
+                m2.reset_state()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                m2.run_em()
+                e1.record()
+                torch.cuda.synchronize()
+                ms2.append(e0.elapsed_time(e1))
+            secondary[tag] = {"value": float(NA) * cols2 * args.max_iter / (ms2[-1] * 1e-3), "unit": "cell-pairs/s",
+                              "ms_per_step": ms2[-1], "columns_per_iteration": int(cols2), "K": int(m2.K),
+                              "note": "EM loop only, device-resident, second of two runs"}
+            del m2
+            torch.cuda.empty_cache()
+    else:
+        sig_final, gam_final = float(m.sigma2), float(m.gamma)
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -460,7 +494,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "aux": {"datagen_s": t_data, "construct_s": t_pre, "coarse_and_variational_init_s": t_init, "init_breakdown": getattr(m, "_timing", None),
-                    "sigma2_final": float(m.sigma2), "gamma_final": float(m.gamma),
+                    "sigma2_final": sig_final, "gamma_final": gam_final, "secondary": secondary,
                     "chain_transforms_gathered": world},
         }
         print(json.dumps(line), flush=True)
