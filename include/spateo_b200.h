@@ -259,6 +259,18 @@ int spb_field_geometry(const spb_field_desc* f, const double* X, int64_t n, cons
                        void* stream); /* GPVectorField.py:12-125,143-190; gaussian_process.py:102-127 */
 
 /* ---- coarse rigid initialisation ---------------------------------------------------------------------------------- */
+/* voxel_data: members of every grid-point ball (radius voxel_size / 2; overlapping) and voxel means. coords [N][D] in
+   float (is_f64 = 0) or double, ax0/ax1/ax2 the np.arange axes in the same dtype (device), lo3 / step3 HOST doubles used
+   only to bracket the candidate grid points; flat voxel index follows np.meshgrid('xy') + reshape(-1, D).
+   spb_voxel_count: counts[nvox] += 1 per member (zero it first). spb_voxel_accumulate: means[new_id[v]][:] +=
+   exp[i][:] / counts[v] (fp64 atomics, zero it first). */
+int spb_voxel_count(const void* coords, int32_t is_f64, int64_t N, int32_t D, const void* ax0, int32_t n0, const void* ax1,
+                    int32_t n1, const void* ax2, int32_t n2, double radius, const double* lo3, const double* step3,
+                    int32_t* counts, void* stream); /* utils.py:1311-1330 */
+int spb_voxel_accumulate(const void* coords, int32_t is_f64, int64_t N, int32_t D, const void* ax0, int32_t n0,
+                         const void* ax1, int32_t n1, const void* ax2, int32_t n2, double radius, const double* lo3,
+                         const double* step3, const int32_t* counts, const int32_t* new_id, const float* exp, int64_t ldg,
+                         int32_t G, double* means, int64_t ldm, void* stream); /* utils.py:1326-1333 */
 /* annealed robust Procrustes over matched pairs, 100 iterations on the device; x, y: [N][3] doubles, dist normalised,
    P in = exp(-dist), out = closing posterior; state: 512 B scratch; out16 = R[9], t[3], sigma2, gamma (device doubles) */
 int spb_inlier_from_nn(const double* x, const double* y, const double* dist, int64_t N, int32_t D, double area, double dmin,

@@ -466,11 +466,17 @@ class Morpho_pairwise:
     # device-side expression distances for small helper problems (coarse init, beta^2 init)
     # ------------------------------------------------------------------------------------------------------------------
     def _raw_cost_T(self, XA_host, XB_host, metric):
-        """E^T[j][i] = metric(A_i, B_j) as a device tensor [nB, ldx_s] (columns beyond nA are padding)."""
+        """E^T[j][i] = metric(A_i, B_j) as a device tensor [nB, ldx_s] (columns beyond nA are padding).
+        Inputs: host arrays or device tensors (the device voxel means are passed straight through)."""
         dev = self._dev
         gc = GeneCostBuilder(self._lib, dev)
-        A = torch.from_numpy(np.ascontiguousarray(XA_host, dtype=np.float32)).to(dev)
-        B = torch.from_numpy(np.ascontiguousarray(XB_host, dtype=np.float32)).to(dev)
+
+        def up(x):
+            if torch.is_tensor(x):
+                return x.to(device=dev, dtype=torch.float32).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+
+        A, B = up(XA_host), up(XB_host)
         opA, rtA, opB, rtB, G = gc.prepare_pair(A, B, metric)
         nA, nB = A.shape[0], B.shape[0]
         lds = _round_up(nA, 256)
@@ -492,8 +498,8 @@ class Morpho_pairwise:
         import time as _time
 
         _t = _time.perf_counter()
-        cA, XA = U.voxel_data(cA, XA, voxel_num=max(min(int(N / 20), 1000), 100))
-        cB, XB = U.voxel_data(cB, XB, voxel_num=max(min(int(M / 20), 1000), 100))
+        cA, XA = self._voxel_data_device(cA, XA, voxel_num=max(min(int(N / 20), 1000), 100))
+        cB, XB = self._voxel_data_device(cB, XB, voxel_num=max(min(int(M / 20), 1000), 100))
         self._timing["coarse.voxel_data_s"] = _time.perf_counter() - _t
         _t = _time.perf_counter()
         metric = "kl" if self.init_field == "layer" else "euc"
@@ -542,6 +548,43 @@ class Morpho_pairwise:
         if self.init_transform:
             self.inlier_A = self.inlier_A @ self.init_R.T + self.init_t
             self.coordsA = self.coordsA @ self.init_R.T + self.init_t
+
+    def _voxel_data_device(self, coords: np.ndarray, gene_exp: np.ndarray, voxel_size=None, voxel_num: int = 10000):
+        """``voxel_data`` (utils.py:1283-1336) on the device: returns (voxel coordinates [n_used, D] numpy, voxel mean
+        expression [n_used, G] float64 DEVICE tensor). The grid axes come from the same ``np.arange`` calls as the
+        reference (host, tiny); membership uses the reference's test in the coordinates' dtype (csrc/voxel.cu)."""
+        dev, lib = self._dev, self._lib
+        N, D = coords.shape
+        if coords.dtype not in (np.float32, np.float64):
+            coords = coords.astype(np.float64)
+        lo, hi = np.min(coords, axis=0), np.max(coords, axis=0)
+        if voxel_size is None:
+            voxel_size = np.sqrt(np.prod(hi - lo)) / (np.sqrt(N) / 5)
+        steps = (hi - lo) / int(np.sqrt(voxel_num))
+        axes = [np.ascontiguousarray(np.arange(a, b, st_), dtype=coords.dtype) for a, b, st_ in zip(lo, hi, steps)]
+        grid = np.stack(np.meshgrid(*axes), axis=-1).reshape(-1, D)
+        radius = float(voxel_size / 2)
+        is_f64 = int(coords.dtype == np.float64)
+        cd = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+        axd = [torch.from_numpy(a).to(dev) for a in axes]
+        while len(axd) < 3:
+            axd.append(axd[0])
+        lo3 = np.zeros(3); lo3[:D] = lo.astype(np.float64)
+        st3 = np.ones(3); st3[:D] = np.maximum(steps.astype(np.float64), 1e-300)
+        n = [len(a) for a in axes] + [1] * (3 - D)
+        counts = torch.zeros((grid.shape[0],), dtype=torch.int32, device=dev)
+        stp = _capi.current_stream_ptr()
+        geom = (ptr(cd), is_f64, N, D, ptr(axd[0]), n[0], ptr(axd[1]), n[1], ptr(axd[2]), n[2], radius, ptr(lo3), ptr(st3))
+        check(lib.spb_voxel_count(*geom, ptr(counts), stp), "spb_voxel_count")
+        used = counts > 0
+        new_id = (torch.cumsum(used.to(torch.int32), 0) - 1).to(torch.int32)
+        n_used = int(used.sum().item())
+        ex = torch.from_numpy(np.ascontiguousarray(gene_exp, dtype=np.float32)).to(dev)
+        G = ex.shape[1]
+        means = torch.zeros((n_used, G), dtype=torch.float64, device=dev)
+        check(lib.spb_voxel_accumulate(*geom, ptr(counts), ptr(new_id), ptr(ex), G, G, ptr(means), G, stp),
+              "spb_voxel_accumulate")
+        return grid[used.cpu().numpy(), :], means
 
     def _inlier_from_NN_device(self, train_x: np.ndarray, train_y: np.ndarray, distance: np.ndarray):
         """``inlier_from_NN`` (utils.py:1220-1280) on the device: returns (P [N,1], R [D,D], t [D], sigma2, gamma)."""

@@ -662,3 +662,27 @@ def test_fused_estep_equals_three_kernel_path(svi, cull, monkeypatch):
         assert abs(sf.sums[q] - su.sums[q]) <= 1e-7 * abs(su.sums[q])  # fp32 partials of a different segment split
     # and the trajectories of the two complete 25-iteration runs agree
     assert np.abs(tf - tu).max() <= 1e-5 * np.abs(tu).max()
+
+
+@pytest.mark.parametrize("dim,dtype,scale", [(2, np.float32, 1.0), (3, np.float32, 1.0), (3, np.float64, 1.0), (3, np.float32, 40.0)])
+def test_voxel_data_device_matches_host(dim, dtype, scale):
+    """Device voxelisation (csrc/voxel.cu) against the host restatement of utils.py:1283-1336: identical non-empty
+    voxels (membership test in the coordinates' dtype), means to fp64 rounding; ``scale`` = un-normalised coordinates,
+    where a cell belongs to hundreds of overlapping voxels."""
+    import spateo_release_b200 as st
+    from oracle import morpho_oracle as mo_
+    from spateo_release_b200.alignment import utils as U
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(1500, 1400, 12, dim=dim, seed=8)
+    m = st.align.Morpho_pairwise(sampleA=B, sampleB=A, verbose=False, device="0", max_iter=1)
+    rng = np.random.default_rng(0)
+    coords = (rng.normal(size=(3000, dim)) * np.array([1.0, 1.0, 0.2][:dim]) * scale).astype(dtype)
+    exp = rng.poisson(2.0, size=(3000, 37)).astype(np.float32)
+    want_c, want_m = U.voxel_data(coords, exp, voxel_num=150)
+    got_c, got_m = m._voxel_data_device(coords, exp, voxel_num=150)
+    got_m = got_m.cpu().numpy()
+    assert got_c.shape == want_c.shape and np.array_equal(got_c, want_c)
+    assert np.abs(got_m - want_m).max() < 1e-11 * max(1.0, np.abs(want_m).max())
+    ref_c, ref_m = mo_.voxel_data(coords, exp, voxel_num=150)  # the oracle's loop restatement (pinned to the reference)
+    assert np.array_equal(got_c, ref_c) and np.abs(got_m - ref_m).max() < 1e-5 * max(1.0, np.abs(ref_m).max())
