@@ -561,11 +561,12 @@ class Morpho_pairwise:
         if voxel_size is None:
             voxel_size = np.sqrt(np.prod(hi - lo)) / (np.sqrt(N) / 5)
         steps = (hi - lo) / int(np.sqrt(voxel_num))
-        axes = [np.ascontiguousarray(np.arange(a, b, st_), dtype=coords.dtype) for a, b, st_ in zip(lo, hi, steps)]
-        grid = np.stack(np.meshgrid(*axes), axis=-1).reshape(-1, D)
+        # np.arange on float32 scalars returns float64, so the reference's `coords - voxel_coord` is evaluated in float64
+        axes = [np.ascontiguousarray(np.arange(a, b, st_), dtype=np.float64) for a, b, st_ in zip(lo, hi, steps)]
+        grid = np.stack(np.meshgrid(*[np.arange(a, b, st_) for a, b, st_ in zip(lo, hi, steps)]), axis=-1).reshape(-1, D)
         radius = float(voxel_size / 2)
-        is_f64 = int(coords.dtype == np.float64)
-        cd = torch.from_numpy(np.ascontiguousarray(coords)).to(dev)
+        is_f64 = 1
+        cd = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(dev)
         axd = [torch.from_numpy(a).to(dev) for a in axes]
         while len(axd) < 3:
             axd.append(axd[0])
