@@ -91,8 +91,8 @@ typedef struct spb_em_params {
   int32_t g_rigid;             /* guidance_effect in ("rigid", "both") */
   int32_t g_NI;                /* number of guidance pairs */
   int32_t sparse_k;            /* > 0: sparse_calculation_mode with sparse_top_k = sparse_k (utils.py:1085-1094) */
-  int32_t fuse_W;              /* > 0: fused persistent E-step with panels of fuse_W columns (multiple of 8 * fuse_nseg) */
-  int32_t fuse_nseg;           /* CTAs per row block in the fused E-step (rowpart must hold fuse_nseg segments) */
+  int32_t reserved0;
+  int32_t reserved1;
   double lambdaVF;
   double gamma_a;
   double gamma_b;
@@ -134,8 +134,6 @@ typedef struct spb_em_params {
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
   int32_t* collist;            /* [ldx/ROW_TILE][nbb_pad] per-row-block column work list */
   int32_t* colcount;           /* [ldx/ROW_TILE] list lengths */
-  int32_t* panel_off;          /* [ldx/ROW_TILE][ceil(NBb/fuse_W) + 1] list position of every panel start (fused E-step) */
-  int32_t* fuse_flags;         /* [2][ceil(NBb/fuse_W)] tickets / ready flags of the fused E-step */
   double* UtWU;                /* [K][K] accumulator */
   double* UtPXB;               /* [K][3] accumulator */
   double* SigmaInv;            /* [K][K] (SVI running average) */
@@ -192,9 +190,6 @@ int spb_estep_col_lists(const spb_em_params* p, void* stream);
 int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1049-1059,1063-1073,1080-1083 (column sums) */
 int spb_col_finalize(const spb_em_params* p, void* stream);               /* utils.py:1053-1055 + denominators */
 int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1059-1083, morpho_class.py:1171-1176,1270,1357 */
-/* sweep 1 + column constants + sweep 2 as ONE persistent cooperative kernel whose second GT read is served by L2
-   (needs fuse_W / fuse_nseg / panel_off / fuse_flags; SPB_EUNSUPPORTED -> use the three calls above) */
-int spb_estep_fused(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1049-1083, morpho_class.py:1171-1176 */
 int spb_row_finalize(const spb_em_params* p, void* stream);
 /* dense P [NA][NBb] (row-major, pitch ldp) of the state left by the last E-step */
 /* sparse_calculation_mode (p->sparse_k > 0): per-column top-k threshold tau_j of the full posterior by an exact radix

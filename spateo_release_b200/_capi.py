@@ -126,7 +126,6 @@ def load_library():
         "spb_col_finalize": ([EP, P], C.c_int),
         "spb_estep_sweep2": ([EP, I32, P], C.c_int),
         "spb_row_finalize": ([EP, P], C.c_int),
-        "spb_estep_fused": ([EP, I32, P], C.c_int),
         "spb_estep_col_select": ([EP, I32, P], C.c_int),
         "spb_sparse_P_emit": ([EP, I32, P, P, P], C.c_int),
         "spb_posterior_argmax": ([EP, I32, P, P, P], C.c_int),

@@ -249,7 +249,6 @@ class Morpho_pairwise:
         compute_mapping: bool = False,
         spatial_sort: bool = True,
         cull_zero_tiles: bool = True,
-        fuse_estep: Optional[bool] = None,
     ) -> None:
         self.verbose = verbose
         self.sampleA, self.sampleB = sampleA, sampleB
@@ -282,9 +281,6 @@ class Morpho_pairwise:
         self.materialize_P = materialize_P
         self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
-        if fuse_estep is None:
-            fuse_estep = os.environ.get("SPB_FUSE_ESTEP", "0") == "1"  # experimental, see DESIGN.md (slower today)
-        self.fuse_estep = bool(fuse_estep)
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64
         self._check()
@@ -753,21 +749,6 @@ class Morpho_pairwise:
                 break
         return seg
 
-    def _choose_fused_geometry(self, nrb: int, nbb: int):
-        """(nseg, W) of the fused persistent E-step, or (0, 0) when it cannot be used: every (row block, segment) CTA
-        must be co-resident (2 CTAs per SM), and a panel of W columns of GT (W * ldx * 4 B) should be a small fraction of
-        the 126 MB L2 so that the panel streamed in step t is still resident when step t + 1 reads it again."""
-        if not self.fuse_estep or self.sparse_calculation_mode:
-            return 0, 0
-        slots = 2 * torch.cuda.get_device_properties(self._dev).multi_processor_count
-        if nrb > slots:
-            return 0, 0
-        nseg = max(1, min(slots // nrb, (nbb + 7) // 8))
-        panel_mb = float(os.environ.get("SPB_FUSE_PANEL_MB", "28"))
-        w_target = panel_mb * 1e6 / (self.ldx * 4.0)
-        cpp = max(8, int(w_target / nseg) // 8 * 8)
-        return nseg, nseg * cpp
-
     def _allocate_state(self):
         dev, D, NA, NB, K, ldx = self._dev, self.D, self.NA, self.NB, self.K, self.ldx
         f32, f64 = torch.float32, torch.float64
@@ -807,14 +788,6 @@ class Morpho_pairwise:
         seg1 = self._choose_segments(nrb, nbb)
         seg2 = self._choose_segments(nrb, nbb)
         seg_alloc = max(seg2, self._choose_segments(nrb, nbb_alloc))
-        fuse_nseg, fuse_W = self._choose_fused_geometry(nrb, nbb)
-        if self.return_mapping and self.SVI_mode:  # the closing full-width E-step runs unfused
-            pass
-        seg_alloc = max(seg_alloc, fuse_nseg)
-        if fuse_W > 0:
-            n_panels = (nbb_alloc + fuse_W - 1) // fuse_W + 1
-            s["panel_off"] = torch.zeros((nrb, n_panels + 1), dtype=torch.int32, device=dev)
-            s["fuse_flags"] = torch.zeros((2, n_panels), dtype=torch.int32, device=dev)
         s["rowpart"] = torch.zeros((seg_alloc, 8, ldx), dtype=f32, device=dev)
         s["bbox"] = torch.zeros((nrb, 8), dtype=f32, device=dev)
         s["collist"] = torch.zeros((nrb, self._nbb_pad), dtype=torch.int32, device=dev)
@@ -856,9 +829,6 @@ class Morpho_pairwise:
         p.seg1, p.seg2, p.nbb_pad, p.trace = seg1, seg2, self._nbb_pad, 1
         p.cull = int(bool(self.cull_zero_tiles))
         p.sparse_k = int(self.sparse_top_k) if self.sparse_calculation_mode else 0
-        p.fuse_W, p.fuse_nseg = fuse_W, fuse_nseg
-        if fuse_W > 0:
-            p.seg2 = fuse_nseg  # row_finalize folds exactly the segments the fused kernel writes
         p.lambdaVF, p.gamma_a, p.gamma_b = float(self.lambdaVF), float(self.gamma_a), float(self.gamma_b)
         p.samples_s = float(self.samples_s)
         p.nn_init_weight = float(self.nn_init_weight)
@@ -904,8 +874,6 @@ class Morpho_pairwise:
             t = s[name]
             setattr(p, name, None if t is None else t.data_ptr())
         p.jacobi_ws = None
-        p.panel_off = s["panel_off"].data_ptr() if "panel_off" in s else None
-        p.fuse_flags = s["fuse_flags"].data_ptr() if "fuse_flags" in s else None
         self._params = p
 
     def _read_scalars(self) -> SpbScalars:
@@ -1005,16 +973,6 @@ class Morpho_pairwise:
         if sweep_events is not None:
             e0, e1, e2, e3 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
             e0.record()
-        if p.fuse_W > 0 and not self.sparse_calculation_mode:
-            rc = lib.spb_estep_fused(C.byref(p), it, st)
-            if rc == 0:
-                if sweep_events is not None:  # one launch covers both sweeps: (start, start, start, end)
-                    e3.record()
-                    sweep_events.append((e0, e0, e0, e3))
-                check(lib.spb_row_finalize(C.byref(p), st), "spb_row_finalize")
-                return
-            if rc != _capi.CONST["SPB_EUNSUPPORTED"]:
-                check(rc, "spb_estep_fused")
         check(lib.spb_estep_sweep1(C.byref(p), it, st), "spb_estep_sweep1")
         if sweep_events is not None:
             e1.record()
@@ -1119,7 +1077,6 @@ class Morpho_pairwise:
             # full (non-SVI) posterior with the final parameters (morpho_class.py:300-302)
             self.SVI_mode = False
             p.svi, p.NBb = 0, self.NB
-            p.fuse_W = 0  # the closing full-width E-step uses the three-kernel path (segment counts differ)
             p.seg1 = p.seg2 = self._choose_segments(self.ldx // _capi.ROW_TILE, self.NB)
             self._NBb = self.NB
             self._estep_only(last_iter, st)

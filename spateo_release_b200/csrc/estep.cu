@@ -144,7 +144,7 @@ __device__ __forceinline__ void butterfly_reduce(float (&acc)[NV], int lane) {
   bfly_step<NV / 32, 1, NV>(acc, lane);
 }
 
-// ---- per-thread state and per-stage math shared by the two-kernel path and the fused persistent kernel --------------
+// ---- per-thread state and per-stage math of the two sweeps --------------
 struct RowRegs {  // 4 consecutive moving cells as two packed pairs (a = rows r, r+1; b = rows r+2, r+3)
   u64 xa0, xb0, xa1, xb1, xa2, xb2, lma, lmb, mma, mmb;
 };
@@ -558,245 +558,6 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Fused persistent E-step: sweep 1, the column constants and sweep 2 in ONE cooperative launch, ordered so that the second
-// read of every GT element comes from L2 instead of HBM.
-// ---------------------------------------------------------------------------------------------------------------------
-// The columns of the iteration are cut into panels of W = nseg * cpp columns (tens of MB of GT, a fraction of the 126 MB
-// L2). CTA (rb, seg) owns row block rb for the whole launch and, in panel p, the seg-th slice of its block's column list
-// inside the panel. Step t of every CTA: phase A(t) = sweep-1 partial column sums of panel t; then phase B(t-1) =
-// sweep-2 row statistics of panel t-1, whose GT rows were streamed one step earlier and are still L2-resident.
-// Between the two, the LAST CTA to finish A(t) (atomic ticket) turns the partial sums of panel t into the column
-// constants (same fp64 fixed-order sum as col_finalize_kernel) and publishes ready[t]; nobody ever waits for work that
-// was not already finished a whole step ago, so the flag latency is hidden. Results are bit-identical to the two-kernel
-// path: same per-thread arithmetic, same column order per CTA, same reduction trees.
-// HBM traffic: 4 B per cell pair per iteration (algorithmic: 8 B); the second 4 B are L2 hits.
-struct FusedArgs {
-  const float* GT;
-  int64_t ldx;
-  const int32_t* col_index;
-  const float* colgeom;
-  float* colconst;
-  const float* XA;
-  const float* lm;
-  const float* mm;
-  const spb_scalars* sc;
-  float* colpart;
-  float* rowpart;
-  float* K_NB;
-  int NBb, nbb_pad, nrb, W, NP;
-  const int32_t* collist;
-  const int32_t* panel_off;  // [nrb][NP + 1] position of the first list entry >= p * W
-  int32_t* flags;            // [2][NP]: tickets of finished A phases, ready flags (zeroed before the launch)
-  int l2_hints;              // 1: phase A loads GT evict_last, phase B evict_first
-};
-
-__device__ __forceinline__ int ld_acquire(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int32_t* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// slice of panel t owned by this CTA: list positions [b, e)
-__device__ __forceinline__ void fused_range(const int32_t* __restrict__ poff, int t, int seg, int nseg, int& b, int& e) {
-  const int lo = poff[t], hi = poff[t + 1];
-  int per = (hi - lo + nseg - 1) / nseg;
-  per = ((per + 7) / 8) * 8;
-  b = min(hi, lo + seg * per);
-  e = min(hi, b + per);
-}
-
-template <int kColStage, int kStages>
-__global__ void __launch_bounds__(kThreads, 2) estep_fused_kernel(const FusedArgs a) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  using Smem = SmemLayoutT<kColStage, kStages>;
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  __shared__ int s_last[2];  // double-buffered by step parity: a fast warp may reach the next ticket early
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rb = blockIdx.x, seg = blockIdx.y, nseg = gridDim.y;
-  const int ncta = gridDim.x * gridDim.y;
-  const int i0 = rb * kRowTile;
-  const int32_t* list = a.collist + (int64_t)rb * a.nbb_pad;
-  const int32_t* poff = a.panel_off + (int64_t)rb * (a.NP + 1);
-  int32_t* ticket = a.flags;
-  int32_t* ready = a.flags + a.NP;
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kConsumers / 32);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  if (warp == kConsumers / 32) {
-    // ---- producer warp: one continuous ring over all phases ----
-    int gst = 0;
-    const uint64_t pol_a = l2_policy_evict_last(), pol_b = l2_policy_evict_first();
-    auto issue = [&](int b, int e, const float* colsrc, int col_floats, int hint) {
-      const int nst = (e - b + kColStage - 1) / kColStage;
-      for (int st = 0; st < nst; ++st, ++gst) {
-        const int s = gst % kStages;
-        if (gst >= kStages) mbar_wait(&sm.empty[s], ((gst / kStages) - 1) & 1);
-        const int pb = b + st * kColStage;
-        if (lane == 0) mbar_expect_tx(&sm.full[s], (uint32_t)(kColStage * kRowTile * 4 + kColStage * col_floats * 4));
-        __syncwarp();
-        if (lane < kColStage) {
-          const bool live = pb + lane < e;
-          const int j = live ? list[pb + lane] : a.NBb;
-          const int jr = live ? j : list[e - 1];
-          const int64_t row = a.col_index ? (int64_t)a.col_index[jr] : (int64_t)jr;
-          if (hint == 0) bulk_g2s(&sm.tile[s][lane][0], a.GT + row * a.ldx + i0, kRowTile * 4, &sm.full[s]);
-          else bulk_g2s_hint(&sm.tile[s][lane][0], a.GT + row * a.ldx + i0, kRowTile * 4, &sm.full[s], hint == 1 ? pol_a : pol_b);
-          bulk_g2s(&sm.cols[s][lane][0], colsrc + (int64_t)j * col_floats, col_floats * 4, &sm.full[s]);
-        }
-      }
-    };
-    for (int t = 0; t <= a.NP; ++t) {
-      int b, e;
-      if (t < a.NP) {
-        fused_range(poff, t, seg, nseg, b, e);
-        issue(b, e, a.colgeom, 8, a.l2_hints ? 1 : 0);
-      }
-      if (t >= 1) {
-        fused_range(poff, t - 1, seg, nseg, b, e);
-        if (b < e) {
-          if (lane == 0) {
-            unsigned long long t0 = 0, now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            while (ld_acquire(ready + (t - 1)) == 0) {
-              __nanosleep(64);
-              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-              if (now - t0 > 4000000000ull) __trap();  // 4 s without progress: abort the launch instead of hanging
-            }
-          }
-          __syncwarp();
-          asm volatile("fence.proxy.async.global;" ::: "memory");  // constants were written through the generic proxy
-          issue(b, e, a.colconst, 16, a.l2_hints ? 2 : 0);
-        }
-      }
-    }
-    return;
-  }
-
-  // ---- consumers ----
-  const u64 CQ = pk(a.sc->c_q, a.sc->c_q), CS = pk(a.sc->c_s, a.sc->c_s);
-  const int r = i0 + tid * 4;
-  const RowRegs R = load_rows(a.XA, a.ldx, a.lm, a.mm, r);
-  S2Acc A;
-  A.clear();
-  int gst = 0, ast = 0;
-  for (int t = 0; t <= a.NP; ++t) {
-    int b, e;
-    if (t < a.NP) {
-      // ---------------- phase A(t): partial column sums ----------------
-      fused_range(poff, t, seg, nseg, b, e);
-      const int nst = (e - b + kColStage - 1) / kColStage;
-      for (int st = 0; st < nst; ++st, ++gst, ++ast) {
-        const int s = gst % kStages;
-        mbar_wait(&sm.full[s], (gst / kStages) & 1);
-        const int pb = b + st * kColStage;
-        constexpr int NV = 4 * kColStage;
-        float acc[NV];
-        sweep1_stage<kColStage, kStages>(sm, s, tid, R, CQ, CS, acc);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);
-        butterfly_reduce<NV>(acc, lane);
-        constexpr int kShift = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);
-        const int buf = ast & 1;
-        if ((lane & ((1 << kShift) - 1)) == 0) sm.red[buf][warp][lane >> kShift] = acc[0];
-        named_bar_sync(1, kConsumers);
-        if (warp == 0 && lane < NV) {
-          float tsum = 0.f;
-#pragma unroll
-          for (int w = 0; w < kConsumers / 32; ++w) tsum += sm.red[buf][w][lane];
-          const int v = lane / kColStage, jj = lane % kColStage;
-          if (pb + jj < e) a.colpart[((int64_t)rb * 4 + v) * a.nbb_pad + list[pb + jj]] = tsum;
-        }
-      }
-      // ticket: the last CTA to finish A(t) owns the column constants of panel t
-      if (warp == 0) {
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) s_last[t & 1] = (atomicAdd(ticket + t, 1) == ncta - 1);
-      }
-      named_bar_sync(1, kConsumers);
-      if (s_last[t & 1]) {
-        __threadfence();
-        const int j0 = t * a.W, j1 = min(a.NBb, j0 + a.W);
-        const double omega = a.sc->omega;
-        for (int jb = j0; jb < j1; jb += kConsumers / 2) {  // warp-uniform trip count: the shuffles below need all lanes
-          // two threads per column: even lane sums C0, C1, odd lane C2, C3 (fp64, row blocks in order)
-          const int j = jb + (tid >> 1);
-          const bool ok = j < j1;
-          const int h = tid & 1;
-          double c0 = 0.0, c1 = 0.0;
-          if (ok) {
-            for (int q = 0; q < a.nrb; ++q) {
-              c0 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h) * a.nbb_pad + j);
-              c1 += (double)__ldcg(a.colpart + ((int64_t)q * 4 + 2 * h + 1) * a.nbb_pad + j);
-            }
-          }
-          const double o0 = __shfl_xor_sync(0xffffffffu, c0, 1), o1 = __shfl_xor_sync(0xffffffffu, c1, 1);
-          if (ok && h == 0) {
-            const double C0 = c0, C1 = c1, C2 = o0, C3 = o1;
-            const double inl = 1.0 - omega / (omega + C0);
-            const double ca = 1.0 / (omega + C1);
-            const double cb = inl / (C2 + 1e-8);
-            const double cc = inl / (C3 + 1e-8);
-            const float* yg = a.colgeom + (int64_t)j * 8;
-            const float y0 = yg[0], y1 = yg[2], y2 = yg[4];
-            const float af = (float)ca, bf = (float)cb, cf = (float)cc;
-            float4* out = reinterpret_cast<float4*>(a.colconst + (int64_t)j * 16);
-            out[0] = make_float4(y0, y0, y1, y1);
-            out[1] = make_float4(y2, y2, af, af);
-            out[2] = make_float4(bf, bf, cf, cf);
-            out[3] = make_float4(0.f, 0.f, 0.f, 0.f);
-            a.K_NB[j] = (float)(cc * C3);
-          }
-        }
-        __threadfence();
-        named_bar_sync(1, kConsumers);
-        if (tid == 0) st_release(ready + t, 1);
-      }
-    }
-    if (t >= 1) {
-      // ---------------- phase B(t-1): row statistics, GT panel read back from L2 ----------------
-      fused_range(poff, t - 1, seg, nseg, b, e);
-      const int nst = (e - b + kColStage - 1) / kColStage;
-      for (int st = 0; st < nst; ++st, ++gst) {
-        const int s = gst % kStages;
-        mbar_wait(&sm.full[s], (gst / kStages) & 1);
-        sweep2_stage<kColStage, kStages, false>(sm, s, tid, R, CQ, CS, A);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);
-      }
-    }
-  }
-  A.store(a.rowpart + ((int64_t)seg * 8) * a.ldx + r, a.ldx);
-}
-
-// panel_off[rb][p] = number of entries of row block rb's column list that are < p * W (p = 0..NP)
-__global__ void panel_offsets_kernel(const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount, int nbb_pad,
-                                     int W, int NP, int32_t* __restrict__ panel_off) {
-  const int rb = blockIdx.y;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p > NP) return;
-  const int32_t* list = collist + (int64_t)rb * nbb_pad;
-  const int n = colcount[rb];
-  const int key = p * W;
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (list[mid] < key) lo = mid + 1;
-    else hi = mid;
-  }
-  panel_off[(int64_t)rb * (NP + 1) + p] = lo;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // sparse_calculation_mode: per-column top-k of the full posterior (utils.py:1085-1094 -> _dense_to_sparse :1369-1404)
 // ---------------------------------------------------------------------------------------------------------------------
 // Within a column P_ij = w_ij c_j with w = q g, so the k largest P are the k largest w. One CTA owns one column (its GT
@@ -1097,7 +858,6 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   if (j0 < j1) atomicMax(rowbest + i, best);
 }
 
-int g_fuse_l2_hints = 0;  // spb_set_sweep_config(10 + h) sets it
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
 template <int C, int S, int B>
@@ -1143,10 +903,6 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
 }
 
 extern "C" int spb_set_sweep_config(int32_t cfg) {
-  if (cfg == 10 || cfg == 11) {  // L2 eviction hints of the fused E-step off / on
-    g_fuse_l2_hints = cfg - 10;
-    return 0;
-  }
   if (cfg < 0 || cfg > 2) return SPB_EINVAL;
   g_sweep_cfg = cfg;
   return 0;
@@ -1239,46 +995,6 @@ extern "C" int spb_posterior_argmax(const spb_em_params* p, int32_t iter, uint64
   return 0;
 }
 
-// Fused persistent E-step (estep_fused_kernel): replaces spb_estep_sweep1 + spb_col_finalize + spb_estep_sweep2.
-// Needs p->fuse_W > 0 (panel width, a multiple of 8 * fuse_nseg), p->panel_off, p->fuse_flags, dense mode, and
-// (ldx / ROW_TILE) * fuse_nseg co-resident CTAs; returns SPB_EUNSUPPORTED otherwise (the caller then uses the 3 kernels).
-extern "C" int spb_estep_fused(const spb_em_params* p, int32_t iter, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
-  if (p->fuse_W <= 0 || p->fuse_nseg <= 0 || p->sparse_k > 0 || !p->panel_off || !p->fuse_flags) return SPB_EUNSUPPORTED;
-  using Smem = SmemLayoutT<8, 3>;
-  static int max_ctas = -1;
-  if (max_ctas < 0) {
-    cudaError_t e = cudaFuncSetAttribute(estep_fused_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    if (e != cudaSuccess) return (int)e;
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, estep_fused_kernel<8, 3>, kThreads, sizeof(Smem));
-    if (e != cudaSuccess) return (int)e;
-    max_ctas = sms * per_sm;
-  }
-  const int nrb = p->ldx / kRowTile;
-  if (nrb * p->fuse_nseg > max_ctas) return SPB_EUNSUPPORTED;
-  const int NP = (p->NBb + p->fuse_W - 1) / p->fuse_W;
-  cudaError_t e = cudaMemsetAsync(p->colpart, 0, sizeof(float) * (size_t)nrb * 4 * p->nbb_pad, st);
-  if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(p->fuse_flags, 0, sizeof(int32_t) * 2 * (size_t)NP, st);
-  if (e != cudaSuccess) return (int)e;
-  panel_offsets_kernel<<<dim3((NP + 1 + 127) / 128, nrb), 128, 0, st>>>(p->collist, p->colcount, p->nbb_pad, p->fuse_W, NP,
-                                                                      p->panel_off);
-  SPB_CHECK_LAUNCH();
-  FusedArgs a;
-  a.GT = p->GT; a.ldx = p->ldx; a.col_index = batch_ptr(p, iter); a.colgeom = p->colgeom; a.colconst = p->colconst;
-  a.XA = p->XAHat; a.lm = p->lm; a.mm = p->mm; a.sc = p->sc; a.colpart = p->colpart; a.rowpart = p->rowpart;
-  a.K_NB = p->K_NB; a.NBb = p->NBb; a.nbb_pad = p->nbb_pad; a.nrb = nrb; a.W = p->fuse_W; a.NP = NP;
-  a.collist = p->collist; a.panel_off = p->panel_off; a.flags = p->fuse_flags; a.l2_hints = g_fuse_l2_hints;
-  void* args[] = {&a};
-  e = cudaLaunchCooperativeKernel((const void*)estep_fused_kernel<8, 3>, dim3(nrb, p->fuse_nseg), dim3(kThreads), args,
-                                  sizeof(Smem), st);
-  if (e != cudaSuccess) return (int)e;
-  SPB_CHECK_LAUNCH();
-  return 0;
-}
 
 extern "C" int spb_row_finalize(const spb_em_params* p, void* stream) {
   row_finalize_kernel<<<(p->NA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(

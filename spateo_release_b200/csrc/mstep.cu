@@ -738,17 +738,10 @@ extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stre
   SPB_TRY(spb_iter_begin(p, iter, stream));
   SPB_TRY(spb_gather_cols(p, iter, stream));
   SPB_TRY(spb_estep_col_lists(p, stream));
-  int fused = SPB_EUNSUPPORTED;
-  if (p->fuse_W > 0 && p->sparse_k <= 0) {
-    fused = spb_estep_fused(p, iter, stream);
-    if (fused != 0 && fused != SPB_EUNSUPPORTED) return fused;
-  }
-  if (fused != 0) {
-    SPB_TRY(spb_estep_sweep1(p, iter, stream));
-    SPB_TRY(spb_col_finalize(p, stream));
-    if (p->sparse_k > 0) SPB_TRY(spb_estep_col_select(p, iter, stream));
-    SPB_TRY(spb_estep_sweep2(p, iter, stream));
-  }
+  SPB_TRY(spb_estep_sweep1(p, iter, stream));
+  SPB_TRY(spb_col_finalize(p, stream));
+  if (p->sparse_k > 0) SPB_TRY(spb_estep_col_select(p, iter, stream));
+  SPB_TRY(spb_estep_sweep2(p, iter, stream));
   SPB_TRY(spb_row_finalize(p, stream));
   SPB_TRY(spb_update_gamma_alpha(p, stream));
   if (nonrigid) {

@@ -615,55 +615,6 @@ def test_kwargs_surface_matches_oracle(name):
     assert errs["float32"][2] < 2e-2
 
 
-@pytest.mark.parametrize("svi", [False, True])
-@pytest.mark.parametrize("cull", [False, True])
-def test_fused_estep_equals_three_kernel_path(svi, cull, monkeypatch):
-    """The fused persistent E-step (one cooperative launch, panel-ordered so the second GT read hits L2) against the
-    sweep1 / col_finalize / sweep2 path on identical state: column constants bit-identical (same per-column reduction
-    tree), row statistics equal up to the fp32 rounding of a different column-to-segment split."""
-    import torch
-
-    import spateo_release_b200 as st
-    from spateo_release_b200.synthetic import make_slice_pair
-
-    monkeypatch.setenv("SPB_FUSE_PANEL_MB", "1.5")  # several panels even at this size
-    A, B = make_slice_pair(5200, 4900, 40, dim=3, seed=6)
-    out = {}
-    for fuse in (False, True):
-        np.random.seed(0)
-        m = st.align.Morpho_pairwise(sampleA=B, sampleB=A, SVI_mode=svi, max_iter=30, nonrigid_start_iter=10, verbose=False,
-                                     device="0", fuse_estep=fuse, cull_zero_tiles=cull, materialize_P=False)
-        m.prepare()
-        assert (m._params.fuse_W > 0) == fuse
-        if fuse:
-            assert (m._NBb + m._params.fuse_W - 1) // m._params.fuse_W >= 3
-        m.run_em(n_iter=25)   # 25 iterations through whichever path
-        stp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        out[fuse] = m
-        torch.cuda.synchronize()
-    # same state -> one more E-step through both paths on the FUSED model's state
-    mf, mu = out[True], out[False]
-    tf, tu = mf._state["trace_buf"][:25, :2].cpu().numpy(), mu._state["trace_buf"][:25, :2].cpu().numpy()
-    for k, v in mf._state.items():
-        if torch.is_tensor(v) and k in mu._state and mu._state[k].shape == v.shape:
-            mu._state[k].copy_(v)
-    stp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    mf._estep_only(25, stp)
-    mu._estep_only(25, stp)
-    torch.cuda.synchronize()
-    n = mf._NBb
-    assert torch.equal(mf._state["colconst"][:n], mu._state["colconst"][:n])
-    assert torch.equal(mf._state["K_NB"][:n], mu._state["K_NB"][:n])
-    for k in ("K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB"):
-        a, b = mf._state[k].double(), mu._state[k].double()
-        assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item(), k
-    sf, su = mf._read_scalars(), mu._read_scalars()
-    for q in range(4):
-        assert abs(sf.sums[q] - su.sums[q]) <= 1e-7 * abs(su.sums[q])  # fp32 partials of a different segment split
-    # and the trajectories of the two complete 25-iteration runs agree
-    assert np.abs(tf - tu).max() <= 1e-5 * np.abs(tu).max()
-
-
 @pytest.mark.parametrize("dim,dtype,scale", [(2, np.float32, 1.0), (3, np.float32, 1.0), (3, np.float64, 1.0), (3, np.float32, 40.0)])
 def test_voxel_data_device_matches_host(dim, dtype, scale):
     """Device voxelisation (csrc/voxel.cu) against the host restatement of utils.py:1283-1336: identical non-empty
