@@ -163,6 +163,13 @@ def cpu_em_sample(n_cells, G, dim, iters, warm=0, steps=1):
     from oracle.morpho_oracle import MorphoPairOracle
     from spateo_release_b200.synthetic import make_slice_pair
 
+    try:  # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
+
     (cA, eA), (cB, eB) = make_slice_pair(n_cells, n_cells, G, dim=dim, seed=0, as_anndata=False,
                                          z_thickness=20.0 if dim == 3 else None)
     np.random.seed(0)
