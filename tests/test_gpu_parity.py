@@ -637,3 +637,32 @@ def test_voxel_data_device_matches_host(dim, dtype, scale):
     assert np.abs(got_m - want_m).max() < 1e-11 * max(1.0, np.abs(want_m).max())
     ref_c, ref_m = mo_.voxel_data(coords, exp, voxel_num=150)  # the oracle's loop restatement (pinned to the reference)
     assert np.array_equal(got_c, ref_c) and np.abs(got_m - ref_m).max() < 1e-5 * max(1.0, np.abs(ref_m).max())
+
+
+def test_sparse_mode_invariants_at_scale():
+    """sparse_calculation_mode at 20k x 20k with the reference's default top_k = 1024 (no oracle at this size): every column
+    stores exactly k entries in descending order, the kept mass is consistent (sum K_NA = sum K_NB = Sp = sum of the COO
+    values), and the alignment agrees with the dense run."""
+    import spateo_release_b200 as st
+    from spateo_release_b200.synthetic import make_slice_pair
+
+    A, B = make_slice_pair(20000, 20000, 64, dim=3, seed=11)
+    kw = dict(SVI_mode=False, max_iter=60, nonrigid_start_iter=30, verbose=False, device="0")
+    np.random.seed(0)
+    ms = st.align.Morpho_pairwise(sampleA=B, sampleB=A, sparse_calculation_mode=True, **kw)
+    P = ms.run()
+    k = 1024
+    assert P.shape == (20000, 20000) and P.nnz == k * 20000
+    v = P.data.reshape(20000, k)
+    assert (np.diff(v, axis=1) <= 0).all() and (v >= 0).all()
+    tot = float(P.data.astype(np.float64).sum())
+    assert abs(ms.K_NA.astype(np.float64).sum() - tot) < 1e-4 * tot
+    assert abs(ms.K_NB.astype(np.float64).sum() - tot) < 1e-4 * tot
+    assert abs(float(ms.Sp) - tot) < 1e-4 * tot
+    colsum = np.asarray(P.sum(0)).ravel()
+    assert np.abs(colsum - ms.K_NB).max() < 1e-4 * max(colsum.max(), 1e-30)
+    np.random.seed(0)
+    md = st.align.Morpho_pairwise(sampleA=B, sampleB=A, materialize_P=False, **kw)
+    md.run()
+    scale = np.abs(md.optimal_RnA).max()
+    assert np.abs(ms.optimal_RnA - md.optimal_RnA).max() < 5e-3 * scale
