@@ -563,7 +563,7 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
 // Within a column P_ij = w_ij c_j with w = q g, so the k largest P are the k largest w. One CTA owns one column (its GT
 // row is contiguous) and finds the k-th largest w EXACTLY by a 3-level radix select on the float bits (12 + 12 + 7 bits;
 // w >= 0 so the bit pattern is monotone). After the first level the surviving candidates are gathered into shared
-// memory, so the column is normally read twice. Per-bin sums give the kept mass without another pass:
+// memory, so the column is normally read twice; that second read also sums the mass above the selected bin:
 //   tau_j   -> colconst[j][12..13]  (sweep 2 keeps pairs with w >= tau_j; exact ties at tau_j are all kept)
 //   K_NB_j  = c_j * sum_{w >= tau_j} w
 // The weight is evaluated with the same instruction sequence as the packed sweep (sub, mul, fma, fma, fma, ex2, mul), so
@@ -605,6 +605,19 @@ __device__ __forceinline__ void sel_for_each(const float* __restrict__ g, const 
   }
 }
 
+// block-wide sum in a fixed order (warp butterfly, then warps in sequence); ends with a barrier so `red` can be reused
+__device__ __forceinline__ float sel_block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < kSelThreads / 32; ++w) t += red[w];
+  __syncthreads();
+  return t;
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                   float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
@@ -634,12 +647,15 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
       sums[t] = 0.f;
     }
     __syncthreads();
+    // level 0 only counts (one shared-memory atomic per non-zero weight); the mass above the selected bin is summed in
+    // registers by the pass that gathers the survivors
+    const bool with_sums = pass > 0;
     auto add = [&](int, float w) {
       const uint32_t key = __float_as_uint(w);
       if (key != 0u && (key & pmask) == prefix) {
         const uint32_t b = (key >> shift) & (uint32_t)(nb - 1);
         atomicAdd(&hist[b], 1u);
-        atomicAdd(&sums[b], w);
+        if (with_sums) atomicAdd(&sums[b], w);
       }
     };
     if (!use_cand) {
@@ -705,7 +721,9 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
     }
     __syncthreads();
     if (sh.total < remaining) {  // fewer non-zero weights than k (only possible at the first level): keep everything
-      kept += sh.total_sum;
+      float acc = 0.f;
+      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int, float w) { acc += w; });
+      kept += sel_block_sum(acc, sh.wsum);
       tau = 0.f;
       break;
     }
@@ -717,20 +735,25 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
       tau = __uint_as_float(prefix);
       break;
     }
-    kept += sh.above_sum;
+    if (pass > 0) kept += sh.above_sum;
     remaining -= sh.above_cnt;
     const uint32_t sel_cnt = sh.sel_cnt;
     __syncthreads();
-    if (!use_cand && sel_cnt <= (uint32_t)kSelCap) {  // gather the survivors once; the remaining levels run from smem
+    if (pass == 0) {
+      // second read of the column: mass of the bins above the selected one (registers, fixed reduction order) and, when
+      // they fit, the survivors of the selected bin into shared memory so the remaining levels never touch global memory
+      const bool fits = sel_cnt <= (uint32_t)kSelCap;
       if (tid == 0) sh.ncand = 0;
       __syncthreads();
+      float acc = 0.f;
       sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int, float w) {
-        const uint32_t key = __float_as_uint(w);
-        if (key != 0u && (key & pmask) == prefix) cand[atomicAdd(&sh.ncand, 1)] = w;
+        const uint32_t kb = __float_as_uint(w) >> 19;
+        if (kb > bsel) acc += w;
+        else if (fits && kb == bsel && w != 0.f) cand[atomicAdd(&sh.ncand, 1)] = w;
       });
-      __syncthreads();
+      kept += sel_block_sum(acc, sh.wsum);
       ncand = sh.ncand;
-      use_cand = true;
+      use_cand = fits;
     }
   }
   if (tid == 0) {
