@@ -32,6 +32,7 @@ extern "C" {
 #define SPB_COL_STAGE 8
 #define SPB_MAX_K_FUSED 64 /* largest K solved by the in-library Jacobi kernel */
 #define SPB_TRACE_STRIDE 8
+#define SPB_COLMASK_WORDS 8 /* per-column bit mask over row blocks (sparse mode): up to 256 row blocks = 262,144 rows */
 
 #define SPB_EINVAL (-2)
 #define SPB_EUNSUPPORTED (-3)
@@ -134,6 +135,7 @@ typedef struct spb_em_params {
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
   int32_t* collist;            /* [ldx/ROW_TILE][nbb_pad] per-row-block column work list */
   int32_t* colcount;           /* [ldx/ROW_TILE] list lengths */
+  uint32_t* colmask;           /* [nbb_pad][SPB_COLMASK_WORDS] sparse mode: row blocks that can hold a non-zero weight, or NULL */
   double* UtWU;                /* [K][K] accumulator */
   double* UtPXB;               /* [K][3] accumulator */
   double* SigmaInv;            /* [K][K] (SVI running average) */

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_PKG_DIR, "libspateo_b200.so")
 
 _SCALAR_TYPES = {
     "int32_t": C.c_int32,
+    "uint32_t": C.c_uint32,
     "int64_t": C.c_int64,
     "float": C.c_float,
     "double": C.c_double,

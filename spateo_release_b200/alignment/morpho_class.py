@@ -792,6 +792,8 @@ class Morpho_pairwise:
         s["bbox"] = torch.zeros((nrb, 8), dtype=f32, device=dev)
         s["collist"] = torch.zeros((nrb, self._nbb_pad), dtype=torch.int32, device=dev)
         s["colcount"] = torch.zeros((nrb,), dtype=torch.int32, device=dev)
+        if self.sparse_calculation_mode:
+            s["colmask"] = torch.zeros((self._nbb_pad, _capi.CONST["SPB_COLMASK_WORDS"]), dtype=torch.int32, device=dev)
         s["UtWU"] = torch.zeros((K, K), dtype=f64, device=dev)
         s["UtPXB"] = torch.zeros((K, 3), dtype=f64, device=dev)
         s["SigmaInv"] = torch.zeros((K, K), dtype=f64, device=dev)
@@ -874,6 +876,7 @@ class Morpho_pairwise:
             t = s[name]
             setattr(p, name, None if t is None else t.data_ptr())
         p.jacobi_ws = None
+        p.colmask = s["colmask"].data_ptr() if "colmask" in s else None
         self._params = p
 
     def _read_scalars(self) -> SpbScalars:

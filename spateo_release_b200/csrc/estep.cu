@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restri
 __global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
                                                                int NBb, spb_scalars* __restrict__ sc, int cull,
                                                                int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
-                                                               int nbb_pad) {
+                                                               int nbb_pad, uint32_t* __restrict__ colmask) {
   __shared__ int warp_cnt[32];
   __shared__ int base;
   const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -501,7 +501,10 @@ __global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __re
     __syncthreads();
     int off = base;
     for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-    if (keep) list[off + __popc(m & ((1u << lane) - 1u))] = j;
+    if (keep) {
+      list[off + __popc(m & ((1u << lane) - 1u))] = j;
+      if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
       int t = 0;
@@ -588,11 +591,17 @@ struct SelShared {
 };
 
 // histogram of (key >> shift) & (nb - 1) over the values whose key matches (prefix, pmask); zero weights are skipped
+// mask (optional): bit rb set <=> row block rb (1024 rows) can hold a non-zero weight for this column; the other blocks
+// are provably all-zero (build_col_lists_kernel) and are skipped — a warp never straddles two row blocks
 template <typename F>
 __device__ __forceinline__ void sel_for_each(const float* __restrict__ g, const float* __restrict__ XA, int64_t ldx,
                                              const float* __restrict__ lm, int NA, float y0, float y1, float y2, float cq,
-                                             F&& f) {
+                                             F&& f, const uint32_t* __restrict__ mask = nullptr) {
   for (int i = threadIdx.x * 4; i < NA; i += kSelThreads * 4) {
+    if (mask != nullptr) {
+      const int rb = i / kRowTile;
+      if (((mask[rb >> 5] >> (rb & 31)) & 1u) == 0u) continue;
+    }
     const float4 G = *reinterpret_cast<const float4*>(g + i);
     const float4 X0 = *reinterpret_cast<const float4*>(XA + i);
     const float4 X1 = *reinterpret_cast<const float4*>(XA + ldx + i);
@@ -621,7 +630,8 @@ __device__ __forceinline__ float sel_block_sum(float v, float* red) {
 __global__ void __launch_bounds__(kSelThreads)
 col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                   float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
-                  const spb_scalars* __restrict__ sc, int NA, int topk, float* __restrict__ K_NB) {
+                  const spb_scalars* __restrict__ sc, int NA, int topk, float* __restrict__ K_NB,
+                  const uint32_t* __restrict__ colmask) {
   extern __shared__ __align__(16) uint8_t sel_raw[];
   uint32_t* hist = reinterpret_cast<uint32_t*>(sel_raw);
   float* sums = reinterpret_cast<float*>(hist + kSelBins);
@@ -634,6 +644,10 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   const float* g = GT + row * ldx;
   const float cq = sc->c_q;
+  __shared__ uint32_t s_mask[SPB_COLMASK_WORDS];
+  if (colmask != nullptr && tid < SPB_COLMASK_WORDS) s_mask[tid] = colmask[(int64_t)jb * SPB_COLMASK_WORDS + tid];
+  __syncthreads();
+  const uint32_t* mask = colmask != nullptr ? s_mask : nullptr;
   uint32_t prefix = 0, pmask = 0, remaining = (uint32_t)min(topk, NA);
   float kept = 0.f;
   bool use_cand = false;
@@ -659,7 +673,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
       }
     };
     if (!use_cand) {
-      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, add);
+      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, add, mask);
     } else {
       for (int t = tid; t < ncand; t += kSelThreads) add(t, cand[t]);
     }
@@ -722,7 +736,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
     __syncthreads();
     if (sh.total < remaining) {  // fewer non-zero weights than k (only possible at the first level): keep everything
       float acc = 0.f;
-      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int, float w) { acc += w; });
+      sel_for_each(g, XA, ldx, lm, NA, y0, y1, y2, cq, [&](int, float w) { acc += w; }, mask);
       kept += sel_block_sum(acc, sh.wsum);
       tau = 0.f;
       break;
@@ -750,7 +764,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
         const uint32_t kb = __float_as_uint(w) >> 19;
         if (kb > bsel) acc += w;
         else if (fits && kb == bsel && w != 0.f) cand[atomicAdd(&sh.ncand, 1)] = w;
-      });
+      }, mask);
       kept += sel_block_sum(acc, sh.wsum);
       ncand = sh.ncand;
       use_cand = fits;
@@ -935,8 +949,14 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
   const int nrb = p->ldx / kRowTile;
   block_bounds_kernel<<<nrb, 256, 0, (cudaStream_t)stream>>>(p->XAHat, p->ldx, p->NA, p->bbox);
   SPB_CHECK_LAUNCH();
+  // sparse mode also records, per column, which row blocks can hold a non-zero weight (col_select skips the others)
+  uint32_t* colmask = (p->sparse_k > 0 && nrb <= 32 * SPB_COLMASK_WORDS) ? p->colmask : nullptr;
+  if (colmask) {
+    cudaError_t e = cudaMemsetAsync(colmask, 0, sizeof(uint32_t) * SPB_COLMASK_WORDS * (size_t)p->nbb_pad, (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+  }
   build_col_lists_kernel<<<nrb, 1024, 0, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
-                                                                 p->colcount, p->nbb_pad);
+                                                                 p->colcount, p->nbb_pad, colmask);
   SPB_CHECK_LAUNCH();
   return 0;
 }
@@ -984,7 +1004,8 @@ extern "C" int spb_estep_col_select(const spb_em_params* p, int32_t iter, void* 
     attr_set = true;
   }
   col_select_kernel<<<p->NBb, kSelThreads, smem, (cudaStream_t)stream>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst,
-                                                                      p->XAHat, p->lm, p->sc, p->NA, p->sparse_k, p->K_NB);
+                                                                      p->XAHat, p->lm, p->sc, p->NA, p->sparse_k, p->K_NB,
+                                                                      (p->cull && p->ldx / kRowTile <= 32 * SPB_COLMASK_WORDS) ? p->colmask : nullptr);
   SPB_CHECK_LAUNCH();
   return 0;
 }
