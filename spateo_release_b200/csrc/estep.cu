@@ -479,31 +479,48 @@ __global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __re
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   int32_t* list = collist + (int64_t)rb * nbb_pad;
-  for (int j0 = 0; j0 < NBb; j0 += 1024) {
-    const int j = j0 + threadIdx.x;
-    bool keep = false;
-    if (j < NBb) {
-      keep = true;
-      if (cull) {
-        const float* y = colgeom + (int64_t)j * 8;
-        float d2 = 0.f;
+  constexpr int kPer = 4;  // columns per thread per round: 4096 columns between block-wide barriers
+  for (int j0 = 0; j0 < NBb; j0 += 1024 * kPer) {
+    const int jt = j0 + threadIdx.x * kPer;
+    unsigned bits = 0u;
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float yd = y[2 * d];
-          const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
-          d2 = fmaf(g, g, d2);
+    for (int q = 0; q < kPer; ++q) {
+      const int j = jt + q;
+      bool keep = false;
+      if (j < NBb) {
+        keep = true;
+        if (cull) {
+          const float* y = colgeom + (int64_t)j * 8;
+          float d2 = 0.f;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float yd = y[2 * d];
+            const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
+            d2 = fmaf(g, g, d2);
+          }
+          keep = cq * d2 >= -127.0f;
         }
-        keep = cq * d2 >= -127.0f;
       }
+      bits |= (keep ? 1u : 0u) << q;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(m);
+    const int c = __popc(bits);
+    int inc = c;  // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_cnt[warp] = inc;
     __syncthreads();
-    int off = base;
+    int off = base + inc - c;
     for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-    if (keep) {
-      list[off + __popc(m & ((1u << lane) - 1u))] = j;
-      if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      if ((bits >> q) & 1u) {
+        const int j = jt + q;
+        list[off++] = j;
+        if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {

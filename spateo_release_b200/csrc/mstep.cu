@@ -82,6 +82,15 @@ __global__ void pxb_term_kernel(spb_em_params p) {
 // U^T diag(K_NA) U  and  U^T PXB_term : 32x32 output tiles, fp64 accumulation, atomics into the K x K accumulator.
 // grid.x = row chunks, grid.y = (kt, lt) tile pairs with kt <= lt.
 constexpr int kAccRows = 128;
+// rows per CTA of weighted_gram_kernel: at least two CTAs per SM in flight even when K <= 32 gives a single tile pair
+inline int gram_rows_per_block(int64_t N, int npairs) {
+  const int64_t want_chunks = (2 * 148 + npairs - 1) / npairs;
+  int64_t rows = (N + want_chunks - 1) / want_chunks;
+  rows = ((rows + kAccRows - 1) / kAccRows) * kAccRows;
+  if (rows < 2 * kAccRows) rows = 2 * kAccRows;
+  if (rows > 2048) rows = 2048;
+  return (int)rows;
+}
 __global__ void __launch_bounds__(256)
 weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const float* __restrict__ w,
                      const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX,
@@ -638,7 +647,7 @@ extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
   SPB_CHECK_LAUNCH();
   const int ntile = (p->K + 31) / 32;
   const int npairs = ntile * (ntile + 1) / 2;
-  int rows_per_block = 2048;
+  const int rows_per_block = gram_rows_per_block(p->NA, npairs);
   dim3 grid((p->NA + rows_per_block - 1) / rows_per_block, npairs);
   weighted_gram_kernel<<<grid, 256, 0, ST>>>(p->UT, p->ldx, p->NA, p->K, p->K_NA, p->PXB_term, p->UtWU, p->UtPXB, rows_per_block, ntile);
   SPB_CHECK_LAUNCH();
@@ -653,7 +662,7 @@ extern "C" int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_
   if (e != cudaSuccess) return (int)e;
   const int ntile = (K + 31) / 32;
   const int npairs = ntile * (ntile + 1) / 2;
-  const int rows_per_block = 2048;
+  const int rows_per_block = gram_rows_per_block(N, npairs);
   dim3 grid((unsigned)((N + rows_per_block - 1) / rows_per_block), npairs);
   weighted_gram_kernel<<<grid, 256, 0, ST>>>(UT, ldx, (int)N, K, w, X3, UtWU, UtX, rows_per_block, ntile);
   SPB_CHECK_LAUNCH();
