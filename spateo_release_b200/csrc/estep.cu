@@ -396,90 +396,6 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   A.store(rowpart + ((int64_t)seg * 8) * ldx + r, ldx);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// sweep 2, narrow variant (spb_set_sweep_config(3)): 512 consumer threads own 2 rows each (one packed pair). Half the
-// per-thread state (7 accumulators, 4 row registers) lets two CTAs of 17 warps share an SM (34 resident warps instead of
-// 18): the v3 profile shows the wide kernel stalled on fixed-latency dependencies with every pipe at 50-67 %.
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int kConsumers2 = kRowTile / 2;   // 512
-constexpr int kThreads2 = kConsumers2 + 32;  // + producer warp
-
-template <int kColStage, int kStages, int kUnroll>
-__global__ void __launch_bounds__(kThreads2, 2)
-estep_sweep2_r2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
-                       const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
-                       const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int nbb_pad,
-                       const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  using Smem = SmemLayoutT<kColStage, kStages>;
-  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rb = blockIdx.x, seg = blockIdx.y;
-  const int i0 = rb * kRowTile;
-  const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
-  const int32_t* list = collist + (int64_t)rb * nbb_pad;
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sm.full[s], 1);
-      mbar_init(&sm.empty[s], kConsumers2 / 32);
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  if (warp == kConsumers2 / 32) {
-    if (cr.begin < cr.end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, list, colconst, 16, i0, cr, NBb, lane);
-    return;
-  }
-  const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
-  const int r = i0 + tid * 2;
-  const float2 X0 = *reinterpret_cast<const float2*>(XA + r);
-  const float2 X1 = *reinterpret_cast<const float2*>(XA + ldx + r);
-  const float2 X2 = *reinterpret_cast<const float2*>(XA + 2 * ldx + r);
-  const float2 LM = *reinterpret_cast<const float2*>(lm + r);
-  const u64 x0 = pk(X0.x, X0.y), x1 = pk(X1.x, X1.y), x2 = pk(X2.x, X2.y), lmp = pk(LM.x, LM.y);
-  const u64 Z = pk(0.f, 0.f);
-  u64 sp = Z, s2 = Z, sd = Z, ka = Z, px = Z, py = Z, pz = Z;
-  const int nst = cr.begin < cr.end ? (cr.end - cr.begin + kColStage - 1) / kColStage : 0;
-  for (int st = 0; st < nst; ++st) {
-    const int s = st % kStages;
-    mbar_wait(&sm.full[s], (st / kStages) & 1);
-#pragma unroll kUnroll
-    for (int jj = 0; jj < kColStage; ++jj) {
-      const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
-      const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
-      const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
-      const u64 g = *reinterpret_cast<const u64*>(&sm.tile[s][jj][tid * 2]);
-      const u64 d = sqdist2(x0, x1, x2, c0.x, c0.y, c1.x);
-      const u64 e = ex2_2(mul2(CS, d));
-      const u64 q = ex2_2(fma2(CQ, d, lmp));
-      sp = fma2(e, c1.y, sp);
-      const u64 t = mul2(q, c2.x);
-      s2 = add2(s2, t);
-      sd = fma2(t, d, sd);
-      const u64 pw = mul2(mul2(q, g), c2.y);
-      ka = add2(ka, pw);
-      px = fma2(pw, c0.x, px);
-      py = fma2(pw, c0.y, py);
-      pz = fma2(pw, c1.x, pz);
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[s]);
-  }
-  float* out = rowpart + ((int64_t)seg * 8) * ldx + r;
-  auto st2 = [&](int qd, u64 v) {
-    float2 f;
-    upk(v, f.x, f.y);
-    *reinterpret_cast<float2*>(out + (int64_t)qd * ldx) = f;
-  };
-  st2(0, sp);
-  st2(1, s2);
-  st2(2, sd);
-  st2(3, ka);
-  st2(4, px);
-  st2(5, py);
-  st2(6, pz);
-}
-
 // per row: fold the segment partials (fp64), write the fp32 statistics, accumulate the global sums
 __global__ void row_finalize_kernel(const float* __restrict__ rowpart, int nseg, int ldx, int NA,
                                     const float* __restrict__ mm, float* __restrict__ K_NA_spatial,
@@ -1028,21 +944,6 @@ int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   return 0;
 }
 
-template <int U>
-int launch_sweep2_r2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
-  using Smem = SmemLayoutT<8, 3>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_r2_kernel<8, 3, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  dim3 grid(p->ldx / kRowTile, p->seg2);
-  estep_sweep2_r2_kernel<8, 3, U><<<grid, kThreads2, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
-                                                                       p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
-  return 0;
-}
-
 }  // namespace
 
 static inline const int32_t* batch_ptr(const spb_em_params* p, int iter) {
@@ -1056,7 +957,7 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
 }
 
 extern "C" int spb_set_sweep_config(int32_t cfg) {
-  if (cfg < 0 || cfg > 4) return SPB_EINVAL;
+  if (cfg < 0 || cfg > 2) return SPB_EINVAL;
   g_sweep_cfg = cfg;
   return 0;
 }
@@ -1101,8 +1002,6 @@ extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
   if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 3) rc = launch_sweep2_r2<2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 4) rc = launch_sweep2_r2<1>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep2<8, 3, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
