@@ -740,12 +740,14 @@ class Morpho_pairwise:
 
     @staticmethod
     def _choose_segments(nrb: int, nbb: int) -> int:
-        """Column segments so that CTAs ~ a multiple of 2 x 148 and a segment is at most ~4096 columns."""
+        """Column segments so that CTAs ~ a multiple of 2 x 148 and a segment is at most ``SPB_MAX_COLS_PER_CTA`` columns
+        (short CTAs keep the tail of the last wave small once culling has shortened the column lists)."""
+        cap = int(os.environ.get("SPB_MAX_COLS_PER_CTA", "4096"))
         max_seg = max(1, nbb // _capi.COL_STAGE)
         seg = 1
-        for waves in range(1, 64):
+        for waves in range(1, 256):
             seg = max(1, min(max_seg, (296 * waves) // max(nrb, 1)))
-            if (nbb + seg - 1) // seg <= 4096 or seg == max_seg:
+            if (nbb + seg - 1) // seg <= cap or seg == max_seg:
                 break
         return seg
 
