@@ -44,6 +44,24 @@ def _round_up(x: int, m: int) -> int:
     return ((x + m - 1) // m) * m
 
 
+class _nvtx:
+    """NVTX range (``SPB_NVTX=1``) around the phases of an alignment, for nsys / ncu --nvtx timelines."""
+
+    enabled = os.environ.get("SPB_NVTX", "0") == "1"
+
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if self.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if self.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def morton_order(coords: np.ndarray) -> np.ndarray:
     """Row permutation that sorts points along a Z-order curve (isotropic quantisation: 16 bits/axis in 2-D, 10 in 3-D)."""
     c = np.asarray(coords, dtype=np.float64)
@@ -1001,7 +1019,8 @@ class Morpho_pairwise:
         with torch.cuda.device(self._dev):
             t0 = _time.perf_counter()
             if self.nn_init:
-                self._coarse_rigid_alignment()
+                with _nvtx("coarse_rigid_alignment"):
+                    self._coarse_rigid_alignment()
             torch.cuda.synchronize()
             self._timing["coarse_rigid_alignment_s"] = _time.perf_counter() - t0
             t0 = _time.perf_counter()
@@ -1015,7 +1034,8 @@ class Morpho_pairwise:
         if not getattr(self, "_host_ready", False):
             self.prepare_host()
         with torch.cuda.device(self._dev):
-            self._build_gene_cost()
+            with _nvtx("expression_cost_matrix"):
+                self._build_gene_cost()
             self._allocate_state()
             check(self._lib.spb_row_update(C.byref(self._params), _capi.current_stream_ptr()), "spb_row_update")
         self._prepared = True
@@ -1045,8 +1065,12 @@ class Morpho_pairwise:
                     hist[it].copy_(self._state["XAHat"])
                     self._state["hist_sigma2"][it].copy_(self._state["sc"][:8].view(torch.float64)[0])
                 last = it == self.max_iter - 1
+                if _nvtx.enabled:
+                    torch.cuda.nvtx.range_push(f"em_iteration_{it}")
                 want_P = (self.materialize_P or self.compute_mapping) and last and not (self.return_mapping and self.SVI_mode)
                 self._iteration(it, st, capture_P=want_P, sweep_events=sweep_events)
+                if _nvtx.enabled:
+                    torch.cuda.nvtx.range_pop()
 
     @torch.no_grad()
     def run(self):
