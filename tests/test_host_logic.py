@@ -111,3 +111,43 @@ def test_label_transfer_defaults():
     assert abs(sum(d["x"].values()) - 1) < 1e-6 and d["x"]["x"] > d["x"]["z"]
     with pytest.raises(KeyError):
         U.check_label_transfer_dict(["x"], ["x", "q"], {"x": {"x": 1.0}})
+
+
+def test_field_desc_layout_and_constants():
+    """The third parsed struct and the new constants agree with the built library."""
+    lib = _capi.load_library()
+    assert lib.spb_sizeof_field_desc() == _capi.C.sizeof(_capi.SpbFieldDesc)
+    names = [f[0] for f in _capi.SpbFieldDesc._fields_]
+    assert names[:4] == ["D", "K", "nonrigid_only", "curvature_formula"] and "mean_transformed" in names
+    assert _capi.CONST["SPB_COLMASK_WORDS"] * 32 * _capi.ROW_TILE >= 262144
+    em = dict(_capi.SpbEmParams._fields_)
+    assert em["colmask"] is _capi.C.c_void_p and em["sparse_k"] is _capi.C.c_int32
+
+
+def test_argmax_key_decoding_and_transpose():
+    """ArgmaxPi.decode inverts the kernels' (float bits << 32 | ~index) key; .T swaps rows and columns."""
+    from spateo_release_b200.alignment.mapping import ArgmaxPi
+
+    vals = np.array([0.0, 1.5e-30, 0.25, 1.0], dtype=np.float32)
+    idx = np.array([0, 7, 99999, 123], dtype=np.int64)
+    keys = (vals.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - idx.astype(np.uint64))
+    arg, val = ArgmaxPi.decode(keys)
+    assert np.array_equal(arg, idx) and np.array_equal(val, vals)
+    # larger value wins; equal values -> lower index wins (what the 64-bit max implements)
+    assert keys[3] > keys[2] > keys[1] > keys[0]
+    k_lo = (np.uint64(vals[2:3].view(np.uint32)[0]) << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - np.uint64(5))
+    assert k_lo > keys[2]
+    pi = ArgmaxPi((3, 2), [1, 0, 1], [0.5, 0.2, 0.0], [0, 2], [0.2, 0.5])
+    t = pi.T
+    assert t.shape == (2, 3) and np.array_equal(t.row_arg, pi.col_arg) and np.array_equal(t.col_val, pi.row_val)
+
+
+def test_segment_choice_respects_the_column_cap(monkeypatch):
+    from spateo_release_b200.alignment.morpho_class import Morpho_pairwise
+
+    seg = Morpho_pairwise._choose_segments(98, 100000)
+    assert (100000 + seg - 1) // seg <= 4096 and seg * 98 >= 296
+    monkeypatch.setenv("SPB_MAX_COLS_PER_CTA", "1024")
+    seg2 = Morpho_pairwise._choose_segments(98, 100000)
+    assert seg2 > seg and (100000 + seg2 - 1) // seg2 <= 1024
+    assert Morpho_pairwise._choose_segments(1, 240) >= 1
