@@ -1,4 +1,9 @@
-"""AnnData-level drivers with the reference signatures (spateo/alignment/morpho_alignment.py:22-454)."""
+"""AnnData-level drivers with the reference signatures (spateo/alignment/morpho_alignment.py:22-454).
+
+The four public functions keep the reference's names, keyword arguments, defaults, return arity and the ``.obsm`` / ``.uns``
+keys they write; the shared steps (input validation, key seeding, running one pair, storing its outputs) live in the small
+helpers below.
+"""
 
 from __future__ import annotations
 
@@ -14,6 +19,8 @@ from .morpho_class import Morpho_pairwise
 from .transform import BA_transform
 from .utils import empty_cache, solve_RT_by_correspondence
 
+Rep = Union[str, List[str]]
+
 
 def _read_h5ad(path):
     try:
@@ -23,123 +30,114 @@ def _read_h5ad(path):
     return ad.read_h5ad(path)
 
 
+def _validate_models(models, models_path):
+    """Input contract of the chain drivers (morpho_alignment.py:146-158, 249-261)."""
+    if models_path is None:
+        assert all(is_anndata_like(m) for m in models), "models should be a list of anndata if models_path is not given."
+        return
+    assert all(isinstance(m, str) for m in models), "models should be a list of file name if models_path is given."
+    assert all(os.path.exists(os.path.join(models_path, m)) for m in models), "Some files in models_path do not exist."
+
+
+def _seed_keys(slices, spatial_key, key_added):
+    """Every slice starts with its raw coordinates under the three result keys (morpho_alignment.py:68-72)."""
+    for sl in slices:
+        for suffix in ("", "_rigid", "_nonrigid"):
+            sl.obsm[key_added + suffix] = sl.obsm[spatial_key].copy()
+
+
+def _solve_pair(fixed, moving, **solver_kwargs):
+    """One ``Morpho_pairwise`` problem: ``moving`` is deformed onto ``fixed``. Returns (solver, P)."""
+    solver = Morpho_pairwise(sampleA=moving, sampleB=fixed, **solver_kwargs)
+    return solver, solver.run()
+
+
+def _store_pair(target, solver, key_added, mode, iter_key_added, vecfld_key_added, coords=None):
+    """Write one pair's outputs onto ``target`` (morpho_alignment.py:96-107). ``coords`` overrides the solver's own
+    (rigid, non-rigid) coordinates (used when the field is carried over to a bigger slice)."""
+    rigid, nonrigid = coords if coords is not None else (solver.optimal_RnA.copy(), solver.XAHat.copy())
+    target.obsm[f"{key_added}_rigid"], target.obsm[f"{key_added}_nonrigid"] = rigid, nonrigid
+    if mode == "SN-S":
+        target.obsm[key_added] = target.obsm[f"{key_added}_rigid"]
+    elif mode == "SN-N":
+        target.obsm[key_added] = target.obsm[f"{key_added}_nonrigid"]
+    if iter_key_added is not None:
+        target.uns[iter_key_added] = solver.iter_added
+    if vecfld_key_added is not None:
+        target.uns[vecfld_key_added] = solver.vecfld
+
+
 def morpho_align(
-    models: List,
-    rep_layer: Union[str, List[str]] = "X",
-    rep_field: Union[str, List[str]] = "layer",
-    genes: Optional[Union[List[str], np.ndarray]] = None,
-    spatial_key: str = "spatial",
-    key_added: str = "align_spatial",
-    iter_key_added: Optional[str] = "iter_spatial",
-    vecfld_key_added: str = "VecFld_morpho",
-    mode: str = "SN-S",
-    dissimilarity: Union[str, List[str]] = "kl",
-    max_iter: int = 200,
-    dtype: str = "float32",
-    device: str = "cpu",
-    verbose: bool = True,
-    **kwargs,
+    models: List, rep_layer: Rep = "X", rep_field: Rep = "layer", genes: Optional[Union[List[str], np.ndarray]] = None,
+    spatial_key: str = "spatial", key_added: str = "align_spatial", iter_key_added: Optional[str] = "iter_spatial",
+    vecfld_key_added: str = "VecFld_morpho", mode: str = "SN-S", dissimilarity: Rep = "kl", max_iter: int = 200,
+    dtype: str = "float32", device: str = "cpu", verbose: bool = True, **kwargs,
 ) -> Tuple[List, List[np.ndarray]]:
     """Serial alignment of consecutive slices; pair i+1 starts from pair i's aligned coordinates
     (morpho_alignment.py:22-111). Returns ``(align_models, pis)`` with ``pis[i] = P.T``."""
-    align_models = [model.copy() for model in models]
-    for m in align_models:
-        m.obsm[key_added] = m.obsm[spatial_key].copy()
-        m.obsm[f"{key_added}_rigid"] = m.obsm[spatial_key].copy()
-        m.obsm[f"{key_added}_nonrigid"] = m.obsm[spatial_key].copy()
+    aligned = [m.copy() for m in models]
+    _seed_keys(aligned, spatial_key, key_added)
     pis = []
-    for i in range(len(align_models) - 1):
-        modelA, modelB = align_models[i], align_models[i + 1]
-        morpho_model = Morpho_pairwise(
-            sampleA=modelB,  # moving
-            sampleB=modelA,  # fixed
-            rep_layer=rep_layer, rep_field=rep_field, dissimilarity=dissimilarity, genes=genes, spatial_key=key_added,
-            key_added=key_added, iter_key_added=iter_key_added, vecfld_key_added=vecfld_key_added, max_iter=max_iter,
-            dtype=dtype, device=device, verbose=verbose, **kwargs,
+    for fixed, moving in zip(aligned[:-1], aligned[1:]):
+        solver, P = _solve_pair(
+            fixed, moving, rep_layer=rep_layer, rep_field=rep_field, dissimilarity=dissimilarity, genes=genes,
+            spatial_key=key_added, key_added=key_added, iter_key_added=iter_key_added, vecfld_key_added=vecfld_key_added,
+            max_iter=max_iter, dtype=dtype, device=device, verbose=verbose, **kwargs,
         )
-        P = morpho_model.run()
-        modelB.obsm[f"{key_added}_rigid"] = morpho_model.optimal_RnA.copy()
-        modelB.obsm[f"{key_added}_nonrigid"] = morpho_model.XAHat.copy()
-        if mode == "SN-S":
-            modelB.obsm[key_added] = modelB.obsm[f"{key_added}_rigid"]
-        elif mode == "SN-N":
-            modelB.obsm[key_added] = modelB.obsm[f"{key_added}_nonrigid"]
-        if iter_key_added is not None:
-            modelB.uns[iter_key_added] = morpho_model.iter_added
-        if vecfld_key_added is not None:
-            modelB.uns[vecfld_key_added] = morpho_model.vecfld
-        pis.append(P.T if P is not None else None)
-        del morpho_model
+        _store_pair(moving, solver, key_added, mode, iter_key_added, vecfld_key_added)
+        pis.append(None if P is None else P.T)
+        del solver
         empty_cache(device=device)
-    return align_models, pis
+    return aligned, pis
 
 
 def pair_transformation(modelA, modelB, spatial_key="spatial", **pairwise_kwargs) -> dict:
     """One link of the chain: align ``modelB`` (moving) onto ``modelA`` (fixed) on RAW coordinates and return the 2-D
     similarity that maps B's raw coordinates onto the aligned ones (morpho_alignment.py:189-211)."""
     pairwise_kwargs.setdefault("materialize_P", False)
-    model = Morpho_pairwise(sampleA=modelB, sampleB=modelA, spatial_key=spatial_key, **pairwise_kwargs)
-    model.run()
-    R, t = solve_RT_by_correspondence(model.optimal_RnA[:, :2], np.asarray(modelB.obsm[spatial_key])[:, :2])
+    solver, _ = _solve_pair(modelA, modelB, spatial_key=spatial_key, **pairwise_kwargs)
+    R, t = solve_RT_by_correspondence(solver.optimal_RnA[:, :2], np.asarray(modelB.obsm[spatial_key])[:, :2])
     return {"Rotation": R, "Translation": t}
 
 
 def morpho_align_transformation(
-    models: List,
-    models_path: Optional[str] = None,
-    save_transformation: bool = False,
-    transformation_path: Optional[str] = "./Spateo_transformation",
-    resume: bool = False,
-    rep_layer: Union[str, List[str]] = "X",
-    rep_field: Union[str, List[str]] = "layer",
-    genes: Optional[Union[List[str], np.ndarray]] = None,
-    spatial_key: str = "spatial",
-    key_added: str = "align_spatial",
-    iter_key_added: Optional[str] = "iter_spatial",
-    vecfld_key_added: str = "VecFld_morpho",
-    dissimilarity: Union[str, List[str]] = "kl",
-    max_iter: int = 200,
-    dtype: str = "float32",
-    device: str = "cpu",
-    verbose: bool = True,
-    **kwargs,
+    models: List, models_path: Optional[str] = None, save_transformation: bool = False,
+    transformation_path: Optional[str] = "./Spateo_transformation", resume: bool = False, rep_layer: Rep = "X",
+    rep_field: Rep = "layer", genes: Optional[Union[List[str], np.ndarray]] = None, spatial_key: str = "spatial",
+    key_added: str = "align_spatial", iter_key_added: Optional[str] = "iter_spatial",
+    vecfld_key_added: str = "VecFld_morpho", dissimilarity: Rep = "kl", max_iter: int = 200, dtype: str = "float32",
+    device: str = "cpu", verbose: bool = True, **kwargs,
 ):
     """Independent pairwise alignments on raw coordinates -> list of {"Rotation", "Translation"} with optional
     per-pair ``.npy`` checkpoints and resume (morpho_alignment.py:114-218)."""
-    if models_path is not None:
-        assert all(isinstance(m, str) for m in models), "models should be a list of file name if models_path is given."
-        assert all(os.path.exists(os.path.join(models_path, m)) for m in models), "Some files in models_path do not exist."
-    else:
-        assert all(is_anndata_like(m) for m in models), "models should be a list of anndata if models_path is not given."
-    iteration, transformation = 0, []
+    _validate_models(models, models_path)
+    from_disk = models_path is not None
+    n_pairs = len(models) - 1
+    checkpoint = (lambda i: os.path.join(transformation_path, f"transformation_{i}.npy"))
+    first, done = 0, []
     if save_transformation:
         Path(transformation_path).mkdir(parents=True, exist_ok=True)
-        if resume:
-            for i in range(len(models) - 1):
-                f = os.path.join(transformation_path, f"transformation_{i}.npy")
-                if os.path.exists(f):
-                    iteration = i
-                    transformation.append(np.load(f, allow_pickle=True))
-        else:
+        if not resume:
             remove_all_files_in_directory(transformation_path)
-    if models_path is not None:
-        modelA = _read_h5ad(os.path.join(models_path, models[iteration]))
-    for i in range(iteration, len(models) - 1):
-        if models_path is not None:
-            modelB = _read_h5ad(os.path.join(models_path, models[i + 1]))
-        else:
-            modelA, modelB = models[i], models[i + 1]
-        cur = pair_transformation(
-            modelA, modelB, spatial_key=spatial_key, rep_layer=rep_layer, rep_field=rep_field,
-            dissimilarity=dissimilarity, genes=genes, key_added=key_added, iter_key_added=iter_key_added,
-            vecfld_key_added=vecfld_key_added, max_iter=max_iter, dtype=dtype, device=device, verbose=verbose, **kwargs,
+        else:  # restart from the highest pair index that has a checkpoint (the reference recomputes that pair)
+            for i in range(n_pairs):
+                if os.path.exists(checkpoint(i)):
+                    first = i
+                    done.append(np.load(checkpoint(i), allow_pickle=True))
+    load = (lambda k: _read_h5ad(os.path.join(models_path, models[k]))) if from_disk else (lambda k: models[k])
+    fixed = load(first)
+    for i in range(first, n_pairs):
+        moving = load(i + 1)
+        link = pair_transformation(
+            fixed, moving, spatial_key=spatial_key, rep_layer=rep_layer, rep_field=rep_field, dissimilarity=dissimilarity,
+            genes=genes, key_added=key_added, iter_key_added=iter_key_added, vecfld_key_added=vecfld_key_added,
+            max_iter=max_iter, dtype=dtype, device=device, verbose=verbose, **kwargs,
         )
-        transformation.append(cur)
+        done.append(link)
         if save_transformation:
-            np.save(os.path.join(transformation_path, f"transformation_{i}.npy"), cur)
-        if models_path is not None:
-            modelA = modelB
-    return transformation
+            np.save(checkpoint(i), link)
+        fixed = moving
+    return done
 
 
 def compose_transformations(transformation: List[dict]):
@@ -156,67 +154,43 @@ def compose_transformations(transformation: List[dict]):
 
 
 def morpho_align_apply_transformation(
-    models: List,
-    models_path: Optional[str] = None,
-    transformation: List[dict] = None,
-    transformation_path: Optional[str] = "./Spateo_transformation",
-    spatial_key: str = "spatial",
-    key_added: str = "align_spatial",
-    save_models_path: Optional[str] = None,
-    verbose: bool = True,
+    models: List, models_path: Optional[str] = None, transformation: List[dict] = None,
+    transformation_path: Optional[str] = "./Spateo_transformation", spatial_key: str = "spatial",
+    key_added: str = "align_spatial", save_models_path: Optional[str] = None, verbose: bool = True,
 ):
     """Apply the composed chain of 2-D similarities to every slice (morpho_alignment.py:221-314)."""
-    if models_path is not None:
-        assert all(isinstance(m, str) for m in models), "models should be a list of file name if models_path is given."
-        assert all(os.path.exists(os.path.join(models_path, m)) for m in models), "Some files in models_path do not exist."
+    _validate_models(models, models_path)
+    from_disk = models_path is not None
+    if transformation is not None:
+        assert len(transformation) == len(models) - 1, "The length of transformation should be len(models) - 1."
     else:
-        assert all(is_anndata_like(m) for m in models), "models should be a list of anndata if models_path is not given."
-    if transformation is None:
         assert os.path.exists(transformation_path), "transformation_path does not exist."
         transformation = [
             np.load(os.path.join(transformation_path, f"transformation_{i}.npy"), allow_pickle=True)
             for i in range(len(models) - 1)
         ]
-    else:
-        assert len(transformation) == len(models) - 1, "The length of transformation should be len(models) - 1."
     if save_models_path is not None:
         Path(save_models_path).mkdir(parents=True, exist_ok=True)
-    align_models = []
-    cur_model = _read_h5ad(os.path.join(models_path, models[0])) if models_path is not None else models[0]
-    cur_model.obsm[key_added] = cur_model.obsm[spatial_key].copy()
-    if save_models_path is not None:
-        cur_model.write(os.path.join(save_models_path, models[0]))
-    elif models_path is not None:
-        align_models.append(cur_model)
-    for i, (cur_R, cur_t) in enumerate(compose_transformations(transformation)):
-        cur_model = _read_h5ad(os.path.join(models_path, models[i + 1])) if models_path is not None else models[i + 1]
-        cur_model.obsm[key_added] = cur_model.obsm[spatial_key].copy() @ cur_R.T + cur_t
+    # slice 0 keeps its coordinates; slice k gets the composition of links 0..k-1
+    placements = [(np.diag((1.0, 1.0)), np.zeros((2,)))] + compose_transformations(transformation)
+    kept = []
+    for k, (R_k, t_k) in enumerate(placements):
+        sl = _read_h5ad(os.path.join(models_path, models[k])) if from_disk else models[k]
+        raw = sl.obsm[spatial_key].copy()
+        sl.obsm[key_added] = raw if k == 0 else raw @ R_k.T + t_k
         if save_models_path is not None:
-            cur_model.write(os.path.join(save_models_path, models[i + 1]))
-        elif models_path is not None:
-            align_models.append(cur_model)
-    return align_models if models_path is not None else models
+            sl.write(os.path.join(save_models_path, models[k]))
+        elif from_disk:
+            kept.append(sl)
+    return kept if from_disk else models
 
 
 def morpho_align_ref(
-    models: List,
-    models_ref: Optional[List] = None,
-    n_sampling: Optional[int] = 2000,
-    sampling_method: str = "random",
-    rep_layer: Union[str, List[str]] = "X",
-    rep_field: Union[str, List[str]] = "layer",
-    genes: Optional[Union[list, np.ndarray]] = None,
-    spatial_key: str = "spatial",
-    key_added: str = "align_spatial",
-    iter_key_added: Optional[str] = "iter_spatial",
-    vecfld_key_added: Optional[str] = "VecFld_morpho",
-    mode: str = "SN-S",
-    dissimilarity: Union[str, List[str]] = "kl",
-    max_iter: int = 200,
-    dtype: str = "float32",
-    device: str = "cpu",
-    verbose: bool = True,
-    **kwargs,
+    models: List, models_ref: Optional[List] = None, n_sampling: Optional[int] = 2000, sampling_method: str = "random",
+    rep_layer: Rep = "X", rep_field: Rep = "layer", genes: Optional[Union[list, np.ndarray]] = None,
+    spatial_key: str = "spatial", key_added: str = "align_spatial", iter_key_added: Optional[str] = "iter_spatial",
+    vecfld_key_added: Optional[str] = "VecFld_morpho", mode: str = "SN-S", dissimilarity: Rep = "kl",
+    max_iter: int = 200, dtype: str = "float32", device: str = "cpu", verbose: bool = True, **kwargs,
 ):
     """Align down-sampled reference models, then carry the learned field to the full models with ``BA_transform``
     (morpho_alignment.py:318-454). Down-sampling: the reference delegates to third-party ``dynamo.tools.sampling``
@@ -227,48 +201,33 @@ def morpho_align_ref(
         models_ref = []
         for m in models:
             n = m.shape[0]
-            idx = np.sort(np.random.choice(n, min(n_sampling, n), replace=False))
-            models_ref.append(m[idx].copy())
+            models_ref.append(m[np.sort(np.random.choice(n, min(n_sampling, n), replace=False))].copy())
+    full = [m.copy() for m in models]
+    small = [m.copy() for m in models_ref]
+    _seed_keys(full + small, spatial_key, key_added)
     pis, pis_ref = [], []
-    align_models = [m.copy() for m in models]
-    align_models_ref = [m.copy() for m in models_ref]
-    for group in (align_models, align_models_ref):
-        for m in group:
-            m.obsm[key_added] = m.obsm[spatial_key].copy()
-            m.obsm[f"{key_added}_rigid"] = m.obsm[spatial_key].copy()
-            m.obsm[f"{key_added}_nonrigid"] = m.obsm[spatial_key].copy()
-    for i in range(len(align_models) - 1):
-        modelA_ref, modelB_ref = align_models_ref[i], align_models_ref[i + 1]
-        morpho_model = Morpho_pairwise(
-            sampleA=modelB_ref, sampleB=modelA_ref, rep_layer=rep_layer, rep_field=rep_field, dissimilarity=dissimilarity,
-            genes=genes, spatial_key=key_added, key_added=key_added, iter_key_added=iter_key_added,
-            vecfld_key_added=vecfld_key_added, max_iter=max_iter, dtype=dtype, device=device, verbose=verbose, **kwargs,
+    for i in range(len(full) - 1):
+        solver, P = _solve_pair(
+            small[i], small[i + 1], rep_layer=rep_layer, rep_field=rep_field, dissimilarity=dissimilarity, genes=genes,
+            spatial_key=key_added, key_added=key_added, iter_key_added=iter_key_added, vecfld_key_added=vecfld_key_added,
+            max_iter=max_iter, dtype=dtype, device=device, verbose=verbose, **kwargs,
         )
-        P = morpho_model.run()
-        modelB_ref.obsm[f"{key_added}_rigid"] = morpho_model.optimal_RnA.copy()
-        modelB_ref.obsm[f"{key_added}_nonrigid"] = morpho_model.XAHat.copy()
-        modelB_ref.obsm[key_added] = modelB_ref.obsm[f"{key_added}_rigid" if mode == "SN-S" else f"{key_added}_nonrigid"]
+        _store_pair(small[i + 1], solver, key_added, mode, iter_key_added, vecfld_key_added)
+        # the same field evaluated on every cell of the full slice
+        nonrigid, _, rigid = BA_transform(vecfld=solver.vecfld, quary_points=full[i + 1].obsm[key_added], device=device,
+                                          dtype=dtype)
+        _store_pair(full[i + 1], solver, key_added, mode, iter_key_added, vecfld_key_added, coords=(rigid, nonrigid))
         pis_ref.append(P)
-        modelB = align_models[i + 1]
-        if iter_key_added is not None:
-            modelB_ref.uns[iter_key_added] = morpho_model.iter_added
-            modelB.uns[iter_key_added] = morpho_model.iter_added
-        if vecfld_key_added is not None:
-            modelB_ref.uns[vecfld_key_added] = morpho_model.vecfld
-            modelB.uns[vecfld_key_added] = morpho_model.vecfld
-        modelB.obsm[f"{key_added}_nonrigid"], _, modelB.obsm[f"{key_added}_rigid"] = BA_transform(
-            vecfld=morpho_model.vecfld, quary_points=modelB.obsm[key_added], device=device, dtype=dtype
-        )
-        modelB.obsm[key_added] = modelB.obsm[f"{key_added}_rigid" if mode == "SN-S" else f"{key_added}_nonrigid"]
         pis.append(P)
-    return align_models, align_models_ref, pis, pis_ref
+    return full, small, pis, pis_ref
 
 
 def remove_all_files_in_directory(directory_path):
-    if os.path.exists(directory_path):
-        for name in os.listdir(directory_path):
-            fp = os.path.join(directory_path, name)
-            if os.path.isfile(fp) or os.path.islink(fp):
-                os.unlink(fp)
-            elif os.path.isdir(fp):
-                shutil.rmtree(fp)
+    if not os.path.exists(directory_path):
+        return
+    for name in os.listdir(directory_path):
+        fp = os.path.join(directory_path, name)
+        if os.path.isdir(fp) and not os.path.islink(fp):
+            shutil.rmtree(fp)
+        else:
+            os.unlink(fp)

@@ -70,3 +70,27 @@ def test_sharded_chain_single_process_equals_serial():
     for a, b in zip(tr_serial, tr):
         assert np.allclose(a["Rotation"], b["Rotation"], atol=1e-6) and np.allclose(a["Translation"], b["Translation"], atol=1e-4)
     assert "align_spatial" in out[2].obsm
+
+
+def test_morpho_align_ref_carries_the_field_to_the_full_slices():
+    """morpho_align_ref (morpho_alignment.py:318-454): align random sub-samples, then place every cell of the full slices
+    with BA_transform; the full slice must land where a direct alignment puts it."""
+    import spateo_release_b200 as st
+
+    models, poses = _chain(n_slices=2, n=3000)
+    np.random.seed(0)
+    full, small, pis, pis_ref = st.align.morpho_align_ref(models, n_sampling=1500, device="0", verbose=False, SVI_mode=False,
+                                                         max_iter=100, mode="SN-S")
+    assert len(full) == 2 and len(small) == 2 and small[1].shape[0] == 1500
+    assert pis_ref[0].shape == (1500, 1500)
+    for key in ("align_spatial", "align_spatial_rigid", "align_spatial_nonrigid"):
+        assert full[1].obsm[key].shape == (3000, 2) and small[1].obsm[key].shape == (1500, 2)
+    assert "VecFld_morpho" in full[1].uns and "iter_spatial" in small[1].uns
+    # slice 0 is untouched; slice 1 is mapped back onto slice 0's frame: compare with the ground-truth positions
+    assert np.array_equal(full[0].obsm["align_spatial"], models[0].obsm["spatial"])
+    R0, s0 = poses[0]
+    truth_in_frame0 = full[1].obsm["truth"] @ R0.T + s0
+    err = np.linalg.norm(full[1].obsm["align_spatial"] - truth_in_frame0, axis=1)
+    assert err.mean() < 1.0, err.mean()
+    with pytest.raises(NotImplementedError):
+        st.align.morpho_align_ref(models, sampling_method="trn", device="0")
