@@ -105,3 +105,18 @@ def load_reference_align_utils():
     load_reference()
     _loaded["au"] = importlib.import_module("spateo.alignment.utils")
     return _loaded["au"]
+
+
+def load_reference_transform():
+    """The unmodified ``spateo/alignment/transform.py`` (BA_transform). Its ``from .methods import ...`` list is served from
+    the already-imported ``methods.utils`` module; names that no longer exist upstream are bound to ``None``."""
+    if "tr" in _loaded:
+        return _loaded["tr"]
+    _, utils = load_reference()
+    pkg = sys.modules["spateo.alignment.methods"]
+    for name in ("_chunk", "_data", "_dot", "_mul", "_pi", "_power", "_prod", "_unsqueeze", "cal_dist", "cal_dot",
+                 "calc_exp_dissimilarity", "check_backend", "check_exp", "con_K", "filter_common_genes", "intersect_lsts"):
+        if not hasattr(pkg, name):
+            setattr(pkg, name, getattr(utils, name, None))
+    _loaded["tr"] = importlib.import_module("spateo.alignment.transform")
+    return _loaded["tr"]

@@ -382,6 +382,26 @@ def test_ba_transform_reproduces_training_points(golden):
     assert np.abs(vel - ov).max() < 1e-9 * scale + 1e-9
 
 
+@pytest.mark.parametrize("tag", ["2d", "3d"])
+def test_ba_transform_matches_reference_fixture(golden, tag):
+    """Product BA_transform on the reference's own vecfld against the unmodified reference's outputs
+    (tests/golden/make_golden_transform.py), default float64 evaluation and both deformation scales."""
+    import spateo_release_b200 as st
+
+    g = golden("ba_transform")
+    vf = {k: g[f"{tag}_vf_{k}"] for k in ("R", "t", "optimal_R", "optimal_t", "init_R", "init_t", "Coff", "inducing_variables")}
+    vf["beta"] = float(g[f"{tag}_vf_beta"])
+    vf["normalize_c"] = bool(g[f"{tag}_vf_normalize_c"])
+    vf["norm_dict"] = {k: g[f"{tag}_nd_{k}"] for k in ("mean_transformed", "mean_fixed", "scale_transformed", "scale_fixed")}
+    pts = g[f"{tag}_points"]
+    scale = np.abs(pts).max()
+    for ds in (1, 0.5):
+        X, V, O = st.align.BA_transform(vf, pts, deformation_scale=ds, device="0")
+        assert np.abs(X - g[f"{tag}_XAHat_float64_{ds}"]).max() < 1e-8 * scale
+        assert np.abs(V - g[f"{tag}_vel_float64_{ds}"]).max() < 1e-8 * scale
+        assert np.abs(O - g[f"{tag}_opt_float64_{ds}"]).max() < 1e-8 * scale
+
+
 def test_morpho_align_driver_and_gp_field(golden):
     import spateo_release_b200 as st
 

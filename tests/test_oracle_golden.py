@@ -113,3 +113,21 @@ def test_ba_transform_reproduces_training_points(golden):
     XAHat, _, opt = mo.ba_transform(orc.vecfld, g["raw_coords_moving"], dtype="float64")
     assert np.abs(XAHat - orc.XAHat).max() < 1e-6 * np.abs(orc.XAHat).max()
     assert np.abs(opt - orc.optimal_RnA).max() < 1e-6 * np.abs(orc.XAHat).max()
+
+
+@pytest.mark.parametrize("tag", ["2d", "3d"])
+def test_ba_transform_matches_reference_fixture(golden, tag):
+    """oracle.ba_transform against outputs of the unmodified reference BA_transform (tests/golden/make_golden_transform.py):
+    bit-identical in float64 and float32, both deformation scales."""
+    g = golden("ba_transform")
+    vf = {k: g[f"{tag}_vf_{k}"] for k in ("R", "t", "optimal_R", "optimal_t", "init_R", "init_t", "Coff", "inducing_variables")}
+    vf["beta"] = float(g[f"{tag}_vf_beta"])
+    vf["normalize_c"] = bool(g[f"{tag}_vf_normalize_c"])
+    vf["norm_dict"] = {k: g[f"{tag}_nd_{k}"] for k in ("mean_transformed", "mean_fixed", "scale_transformed", "scale_fixed")}
+    pts = g[f"{tag}_points"]
+    for dt in ("float64", "float32"):
+        for ds in (1, 0.5):
+            X, V, O = mo.ba_transform(vf, pts, deformation_scale=ds, dtype=dt)
+            sfx = f"{dt}_{ds}"
+            assert np.array_equal(X, g[f"{tag}_XAHat_{sfx}"]) and X.dtype == g[f"{tag}_XAHat_{sfx}"].dtype
+            assert np.array_equal(V, g[f"{tag}_vel_{sfx}"]) and np.array_equal(O, g[f"{tag}_opt_{sfx}"])
