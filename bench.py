@@ -5,16 +5,22 @@ Workload (default, = BASELINE configs[1]): one synthetic 3-D slice pair per GPU,
 KL dissimilarity, full EM (SVI_mode=False), K=15 inducing points, nn_init=True, max_iter=200. A *step* is one complete
 200-iteration EM over one slice pair.
 
-  value  = (N_A * N_B * max_iter * n_gpus) / (max-over-ranks device time of one step), cost matrix resident in HBM
-           (EM loop only; preprocess, coarse init, cost precompute and P materialisation excluded).
-  e2e    = the same pairs divided by the time of the public-API path from PINNED HOST buffers: H2D of expression and
-           coordinates, expression-cost precompute, the EM loop, closing similarity and D2H of every result.
-  roofline = E-step sweep kernels: 4 B per cell pair per sweep (algorithmic) / CUDA-event time of each launch, against
-           MEASURED_PEAKS.json hbm_gbs.
+  value        = (N_A * N_B * max_iter * n_gpus) / (max-over-ranks device time of one step), cost matrix resident in HBM
+                 (EM loop only), product defaults (exact zero-tile culling on).
+  value_dense  = the same loop with culling off: every sweep launch reads all N_A x N_B pairs (the plain 8 B/pair figure).
+  e2e          = the same pairs divided by the wall time of the PUBLIC call ``st.align.morpho_align([A, B], ...)`` on
+                 plain (unpinned) host arrays: slice copies, constructor, coarse rigid + variational initialisation,
+                 H2D of expression and coordinates, expression-cost precompute, the EM loop, closing similarity, D2H of
+                 every result. ``e2e.device_only`` keeps the narrower figure (H2D + cost matrix + EM + D2H on a
+                 pre-constructed solver with pinned inputs).
+  roofline     = E-step sweep kernels: 4 B per cell pair per sweep (algorithmic) / CUDA-event time of each launch, against
+                 MEASURED_PEAKS.json hbm_gbs; ``roofline_dense`` = the culling-off launches.
   cpu_baseline = the numpy oracle (port of the reference CPU path) on a bounded sample, host cores stated.
 
 ``--impl reference`` times the reference's CPU algorithm (oracle port; the reference itself is pure Python and
-/root/reference does not exist on the GPU box) with all host threads on a bounded sample of the same workload.
+/root/reference does not exist on the GPU box) on a bounded sample: ONE EM iteration of a 20,000 x 20,000 pair per step
+(BASELINE.md section 4), W + K steps really executed; its ``config`` describes that sample.
+Other workloads: ``--workload vfc`` (BASELINE configs[4]), ``--workload chain`` (configs[2], multi-GPU slice chain).
 Multi-GPU (torchrun): one independent slice pair per rank (weak scaling) + ONE all-gather of the per-pair rigid
 transforms per step for the chain composition.
 """
@@ -46,9 +52,10 @@ def parse_args():
     ap.add_argument("--max-iter", type=int, default=200)
     ap.add_argument("--K", type=int, default=15)
     ap.add_argument("--svi", action="store_true", help="default SVI mode (batch = N_B/10) instead of the full EM")
-    ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-cells", type=int, default=6000, help="cells per slice of the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-iters", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-cells", type=int, default=20000, help="cells per slice of the bounded CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=1, help="EM iterations per step of the CPU sample")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2, help="steps of the cpu_baseline leg of the b200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary EM-loop timings (default SVI mode; K=200 inducing points) of SURVEY.md 8(d) config 2")
@@ -61,7 +68,7 @@ def parse_args():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# synthetic data generated on the device, staged to pinned host memory
+# synthetic data generated on the device, returned as plain host arrays
 # ---------------------------------------------------------------------------------------------------------------------
 def make_pair_on_device(n, G, dim, seed, device):
     import torch
@@ -89,19 +96,13 @@ def make_pair_on_device(n, G, dim, seed, device):
     R[0, 0], R[0, 1], R[1, 0], R[1, 1] = np.cos(th), -np.sin(th), np.sin(th), np.cos(th)
     coordsB = base @ R.T + 5.0 + torch.randn((n, dim), generator=g, device=device, dtype=torch.float64) * 0.3
 
-    def pinned(t):
-        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        h.copy_(t)
-        return h
-
-    hA, hB = pinned(expA), pinned(expB)
-    torch.cuda.synchronize()
     import pandas as pd
 
     var = pd.DataFrame(index=[f"g{i}" for i in range(G)])
-    A = AnnDataLite(hA.numpy(), var=var.copy(), obsm={"spatial": coords.cpu().numpy()})
-    B = AnnDataLite(hB.numpy(), var=var.copy(), obsm={"spatial": coordsB.cpu().numpy()})
-    A._pin, B._pin = hA, hB  # keep the pinned storage alive
+    # plain (pageable) host arrays, as a user's AnnData holds them
+    A = AnnDataLite(expA.cpu().numpy(), var=var.copy(), obsm={"spatial": coords.cpu().numpy()})
+    B = AnnDataLite(expB.cpu().numpy(), var=var.copy(), obsm={"spatial": coordsB.cpu().numpy()})
+    torch.cuda.synchronize()
     return A, B
 
 
@@ -159,7 +160,8 @@ class ClockSampler:
 # CPU baseline: the oracle port of the reference's numpy path on a bounded sample
 # ---------------------------------------------------------------------------------------------------------------------
 def cpu_em_sample(n_cells, G, dim, iters, warm=0, steps=1):
-    """Returns (pairs_per_sec, seconds_per_step, description). EM loop only, cost matrix precomputed (like `value`)."""
+    """Returns (pairs_per_sec, seconds_per_step, description, steps_executed). EM loop only, cost matrix precomputed (like
+    `value`); every step runs ``iters`` further iterations of the same EM."""
     from oracle.morpho_oracle import MorphoPairOracle
     from spateo_release_b200.synthetic import make_slice_pair
 
@@ -173,7 +175,8 @@ def cpu_em_sample(n_cells, G, dim, iters, warm=0, steps=1):
     (cA, eA), (cB, eB) = make_slice_pair(n_cells, n_cells, G, dim=dim, seed=0, as_anndata=False,
                                          z_thickness=20.0 if dim == 3 else None)
     np.random.seed(0)
-    o = MorphoPairOracle(cB, cA, [eB], [eA], dtype="float32", SVI_mode=False, max_iter=iters, K=15, nn_init=False)
+    o = MorphoPairOracle(cB, cA, [eB], [eA], dtype="float32", SVI_mode=False, max_iter=iters * (warm + steps), K=15,
+                         nn_init=False)
     o.prepare()
     times = []
     it = 0
@@ -185,9 +188,22 @@ def cpu_em_sample(n_cells, G, dim, iters, warm=0, steps=1):
         times.append(time.perf_counter() - t0)
     sec = float(np.mean(times[warm:]))
     pairs = float(n_cells) * n_cells * iters
-    desc = (f"oracle port of Morpho_pairwise EM (float32 numpy, SVI off, nn_init off), {n_cells}x{n_cells} cells, "
-            f"{G} genes, {dim}-D, {iters} EM iterations per step, cost matrix precomputed")
-    return pairs / sec, sec, desc
+    desc = (f"oracle port of Morpho_pairwise EM (float32 numpy as in the reference: BLAS calls threaded, element-wise passes "
+            f"single-threaded; SVI off, nn_init off), {n_cells}x{n_cells} cells, {G} genes, {dim}-D, {iters} EM iteration(s) per "
+            f"step, {warm}+{steps} steps executed, cost matrix precomputed")
+    return pairs / sec, sec, desc, warm + steps
+
+
+def reference_config(args):
+    """What the reference arm really runs: a bounded sample of configs[1] (SURVEY.md 8(d) 'CPU baseline timing')."""
+    return {
+        "workload": f"bounded CPU sample of the morpho_align pair workload: 2 synthetic {args.dim}-D slices, {args.cpu_cells} cells "
+                    f"each, {args.genes} genes, KL, full EM (SVI_mode=False), K=15, nn_init=False; one step = {args.cpu_iters} EM "
+                    f"iteration(s) (the 100000-cell pair needs 7 live N x M fp32 temporaries = 280 GB in the reference's "
+                    f"get_P_core and does not fit the host; pairs/s is size-independent to first order)",
+        "cells_per_slice": args.cpu_cells, "genes": args.genes, "dim": args.dim, "em_iterations_per_step": args.cpu_iters,
+        "K": 15, "svi": False, "nn_init": False, "sample_of": "BASELINE configs[1] (100000 cells per slice, 200 iterations)",
+    }
 
 
 def run_reference_arm(args):
@@ -195,16 +211,17 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count()
-    v, sec, desc = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters, warm=min(args.warmup, 1),
-                                 steps=max(1, min(args.steps, 3)))
+    v, sec, desc, executed = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters, warm=args.warmup,
+                                           steps=args.steps)
     line = {
         "impl": "reference",
         "metric": "cell-pairs/sec through morpho_align EM", "value": v, "unit": "cell-pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "steps": args.steps, "warmup": args.warmup, "steps_executed": executed, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": reference_config(args),
         "cpu_baseline": {"value": v, "unit": "cell-pairs/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": v, "unit": "cell-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "one CPU process on rank 0 regardless of --gpus: at N > 1 compare per GPU, not the N-GPU aggregate",
     }
     print(json.dumps(line), flush=True)
 
@@ -319,9 +336,9 @@ def main():
     t_pre = time.perf_counter() - t0
     t0 = time.perf_counter()
     m.prepare_host()
-    m.pin_inputs()
     torch.cuda.synchronize()
     t_init = time.perf_counter() - t0
+    m.pin_inputs()
 
     NA, NB = m.NA, m.NB
     cols = m.batch_size if args.svi else NB
@@ -339,10 +356,52 @@ def main():
         else:
             gathered[0].copy_(m._state["optimal"])
 
-    # ---- end-to-end arm first (public API, pinned host buffers in, numpy results out) ----
+    # ---- end-to-end arm 1: the PUBLIC call on plain host arrays (what a user of the reference types) ----
+    from spateo_release_b200.alignment import morpho_class as _mc
+
+    def public_call():
+        np.random.seed(rank)
+        aligned, pis = st.align.morpho_align(
+            [A, B], device=str(local_rank), verbose=False, SVI_mode=bool(args.svi), max_iter=args.max_iter, K=args.K,
+            nn_init=True, mode="SN-N", materialize_P=False, iter_key_added=None,
+        )
+        vf = aligned[1].uns["VecFld_morpho"]
+        mine = torch.zeros(12, dtype=torch.float64)
+        D_ = vf["optimal_R"].shape[0]
+        mine[:9].view(3, 3)[:D_, :D_] = torch.from_numpy(np.asarray(vf["optimal_R"], dtype=np.float64))
+        mine[9:9 + D_] = torch.from_numpy(np.asarray(vf["optimal_t"], dtype=np.float64).reshape(-1))
+        mine = mine.to(dev)
+        if world > 1:  # the chain's single exchange: every pair's closing similarity
+            dist.all_gather(gathered, mine)
+        else:
+            gathered[0].copy_(mine)
+        res = np.asarray(aligned[1].obsm["align_spatial"])  # host numpy: the result the caller reads
+        assert np.isfinite(res).all()
+        return res
+
+    pub_times = []
+    pub_h2d = pub_d2h = 0
+    m.__dict__.pop("_GT", None)
+    m.__dict__.pop("_state", None)
+    torch.cuda.empty_cache()
+    for s in range(1 + max(args.e2e_steps, 1)):
+        _mc.TRANSFER_BYTES["h2d"] = _mc.TRANSFER_BYTES["d2h"] = 0
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        public_call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= 1:
+            pub_times.append(max_over_ranks(dt))
+        pub_h2d, pub_d2h = _mc.TRANSFER_BYTES["h2d"], _mc.TRANSFER_BYTES["d2h"]
+    pub_sec = float(np.mean(pub_times))
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end arm 2 (narrower, kept for continuity): pre-constructed solver, pinned inputs ----
     e2e_times = []
     h2d = d2h = 0
-    for s in range(1 + max(args.e2e_steps, 1)):
+    for s in range(1 + 2):
         m._prepared = False
         m.__dict__.pop("_GT", None)
         m.__dict__.pop("_state", None)
@@ -484,19 +543,30 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, sec, desc = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters)
+            v, sec, desc, _n = cpu_em_sample(args.cpu_cells, args.genes, args.dim, args.cpu_iters, warm=0,
+                                             steps=args.cpu_baseline_steps)
             cpu = {"value": v, "unit": "cell-pairs/s", "cores": os.cpu_count(), "kind": "port", "sample": desc,
-                   "seconds": sec}
+                   "seconds_per_step": sec}
         line = {
             "metric": "cell-pairs/sec through morpho_align EM", "value": value, "unit": "cell-pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
             "clocks": clocks,
-            "e2e": {"value": pairs_per_step * world / e2e_sec, "unit": "cell-pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "seconds_per_step": e2e_sec, "steps": len(e2e_times),
-                    "includes": "H2D(pinned) of expression+coords, expression-cost precompute, EM loop, closing "
-                                "similarity, all-gather, D2H of results; excludes coarse rigid init / sigma2 / beta2 init"},
+            "value_dense": roofline["dense"]["value"],
+            "e2e": {"value": pairs_per_step * world / pub_sec, "unit": "cell-pairs/s", "h2d_bytes_per_step": int(pub_h2d),
+                    "d2h_bytes_per_step": int(pub_d2h), "seconds_per_step": pub_sec, "steps": len(pub_times),
+                    "call": "st.align.morpho_align([A, B], device=..., SVI_mode=False, max_iter=200, K=15, nn_init=True, "
+                            "mode='SN-N', materialize_P=False, iter_key_added=None) on plain (pageable) host arrays",
+                    "includes": "slice copies, Morpho_pairwise constructor (gene intersection, dense extraction, "
+                                "normalisation, inducing kernel), coarse rigid + variational initialisation, H2D of "
+                                "expression and coordinates, expression-cost precompute, EM loop, closing similarity, "
+                                "all-gather, D2H of the aligned coordinates and vectors",
+                    "device_only": {"value": pairs_per_step * world / e2e_sec, "seconds_per_step": e2e_sec,
+                                    "steps": len(e2e_times), "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                                    "includes": "pre-constructed solver, pinned inputs: H2D, expression-cost precompute, "
+                                                "EM loop, closing similarity, all-gather, D2H of results"}},
+            "roofline_dense": roofline["dense"],
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu,

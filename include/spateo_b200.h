@@ -30,6 +30,7 @@ extern "C" {
 
 #define SPB_ROW_TILE 1024
 #define SPB_COL_STAGE 8
+#define SPB_COLCONST_FLOATS 20 /* per-column constant record of sweep 2 (see spb_em_params.colconst) */
 #define SPB_MAX_K_FUSED 64 /* largest K solved by the in-library Jacobi kernel */
 #define SPB_TRACE_STRIDE 8
 #define SPB_COLMASK_WORDS 8 /* per-column bit mask over row blocks (sparse mode): up to 256 row blocks = 262,144 rows */
@@ -129,7 +130,7 @@ typedef struct spb_em_params {
   float* PXB_term;             /* [3][ldx] (SVI running average) */
   float* K_NB;                 /* [NBb] */
   float* colgeom;              /* [nbb_pad][8] (y0,y0,y1,y1,y2,y2,0,0): this iteration's columns, duplicated for f32x2 */
-  float* colconst;             /* [nbb_pad][16] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, tau,tau,0,0); zero beyond NBb */
+  float* colconst;             /* [nbb_pad][SPB_COLCONST_FLOATS] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, cy0,cy0,cy1,cy1, cy2,cy2,tau,tau); zero beyond NBb */
   float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
   float* rowpart;              /* [seg2][8][ldx] partial row statistics */
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
@@ -143,6 +144,14 @@ typedef struct spb_em_params {
   double* Coff;                /* [K][3] */
   double* moments;             /* [32] rigid-update moment accumulator */
   double* jacobi_ws;           /* [2*K*K + 2*K] workspace of the eigen-solver */
+  const float* UT_hi;          /* [K][ldx] tf32 split of the row-centred UT (tensor-core K^T P K contraction), or NULL = SIMT path */
+  const float* UT_lo;          /* [K][ldx] */
+  const float* UT_mean;        /* [K] row means of UT (spb_gram_center) */
+  float* GB_hi;                /* [K+4][ldx] per-iteration B operand [K_NA o D ; PXB_term^T ; K_NA], hi part */
+  float* GB_lo;                /* [K+4][ldx] */
+  double* gram_sums;           /* [4] sum K_NA, sum_n PXB_term[e] */
+  float* gram_scratch;         /* slice partials of the tensor-core contraction (spb_gram_tc_scratch_floats) */
+  int64_t gram_scratch_floats;
   const double* g_XA;          /* [g_NI][3] normalised guidance points on the moving slice */
   const double* g_XB;          /* [g_NI][3] ... on the fixed slice */
   double* g_VA;                /* [g_NI][3] V_AI = U_I Coff */
@@ -179,6 +188,23 @@ int spb_gene_cost_tc(const float* A_hi, const float* A_lo, int64_t lda, const fl
                      const float* B_lo, int64_t ldb, const float* rowtermB, int64_t NA, int64_t NB, int64_t G, int32_t metric,
                      int32_t prob_type, float prob_param, int32_t accumulate, float* GT, int64_t ldx,
                      void* stream); /* utils.py:697,780-783,742 + :977-981 */
+/* ---- K^T P K contraction on tcgen05 (3xTF32, fp32 accumulate per <= 4096-element slice, fp64 fold) ----------------------
+   UtWU[k][l] = sum_n UT[k][n] w[n] UT[l][n]  (morpho_class.py:1266-1268; SparseVFC U^T P U, sparsevfc.py:189-198)
+   UtX[k][e]  = sum_n UT[k][n] X[e][n], e < E <= 3  (morpho_class.py:1279)
+   The tensor core's fp32 accumulator truncates, so the contraction runs on the row-centred kernel D = UT - mean (signed
+   terms) and the rank-one corrections are added back in fp64:
+     spb_gram_center  (once; UT is constant over the EM): mean[K], A_hi/A_lo = tf32 split of D            [K][ldn]
+     spb_gram_prepare (every iteration): B_hi/B_lo rows k < K = w o D[k], rows K..K+E-1 = X[e], row K+E = w  [K+E+1][ldn]
+                      and sums4 = (sum w, sum_n X[0], X[1], X[2]) in fp64
+     spb_gram_tc      : the GEMM + fp64 reduction -> UtWU [K][K] (exactly symmetric), UtX [K][3]
+   K + E + 1 <= 1024; scratch size from spb_gram_tc_scratch_floats. */
+int spb_gram_tc_scratch_floats(int32_t K, int32_t E, int64_t N, int64_t* floats);
+int spb_gram_center(const float* UT, int64_t ldn, int64_t N, int32_t K, float* mean, float* A_hi, float* A_lo, void* stream);
+int spb_gram_prepare(const float* UT, int64_t ldn, int64_t N, int32_t K, const float* mean, const float* w, const float* X,
+                     int64_t ldxx, int32_t E, float* B_hi, float* B_lo, double* sums4, void* stream);
+int spb_gram_tc(const float* A_hi, const float* A_lo, const float* B_hi, const float* B_lo, int64_t ldn, int64_t N, int32_t K,
+                int32_t E, const float* mean, const double* sums4, float* scratch, int64_t scratch_floats, double* UtWU,
+                double* UtX, void* stream);
 /* label layer: GT[j][i] (op)= LT[labA_i][labB_j] */
 int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, int32_t nB_labels, int64_t NA, int64_t NB,
                    int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:830 */
@@ -195,7 +221,7 @@ int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* uti
 int spb_row_finalize(const spb_em_params* p, void* stream);
 /* dense P [NA][NBb] (row-major, pitch ldp) of the state left by the last E-step */
 /* sparse_calculation_mode (p->sparse_k > 0): per-column top-k threshold tau_j of the full posterior by an exact radix
-   select (one CTA per column), written to colconst[j][12..13]; K_NB_j becomes the kept mass. Call between
+   select (one CTA per column), written to colconst[j][18..19]; K_NB_j becomes the kept mass. Call between
    spb_col_finalize and spb_estep_sweep2 (spb_em_iteration does). */
 int spb_estep_col_select(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1085-1094,1369-1404 */
 /* COO entries of the sparse posterior of the last E-step: rows[NBb][sparse_k], vals[NBb][sparse_k] (unordered inside a

@@ -145,6 +145,49 @@ def get_P_core(
     return P, K_NA_spatial, K_NA_sigma2, sigma2_related
 
 
+def estep_column_chunks(
+    Dim, XAHat, YB, exp_A, exp_B, metric, sigma2, model_mul, gamma, samples_s, sigma2_variance, probability_type,
+    probability_parameters, chunk=1000, label_transfer=None, keep_P=False,
+):
+    """One full E-step evaluated in COLUMN CHUNKS (for sizes whose N_A x N_B temporaries do not fit the host).
+
+    Every normalisation inside ``get_P_core`` is a per-column sum over the moving cells (utils.py:1053-1083), so a block of
+    columns is an independent sub-problem as long as ``outlier_s`` keeps the full N_A (it does: spatial_dist.shape[0]).
+    Each chunk goes through the very same ``calc_distance`` / ``get_P_core`` as ``MorphoPairOracle._update_assignment_P``
+    (morpho_class.py:1147-1176); row statistics are accumulated across chunks.
+
+    Returns a dict with K_NA, K_NB, K_NA_spatial, K_NA_sigma2, PXB, sigma2_related_num, Sp (and P when ``keep_P``).
+    """
+    XAHat = np.asarray(XAHat)
+    NA, NB = XAHat.shape[0], YB.shape[0]
+    out = dict(
+        K_NA=np.zeros(NA), K_NB=np.zeros(NB), K_NA_spatial=np.zeros(NA), K_NA_sigma2=np.zeros(NA),
+        PXB=np.zeros((NA, YB.shape[1])), sigma2_related_num=0.0,
+    )
+    blocks = []
+    for j0 in range(0, NB, chunk):
+        j1 = min(NB, j0 + chunk)
+        spatial = euc_distance(XAHat, YB[j0:j1], squared=True)
+        ed = calc_distance(exp_A, [e[j0:j1] for e in exp_B], metric, label_transfer)
+        P, kns, kn2, s2r = get_P_core(
+            Dim=Dim, spatial_dist=spatial, exp_dist=ed, sigma2=sigma2, model_mul=model_mul, gamma=gamma,
+            samples_s=samples_s, sigma2_variance=sigma2_variance, probability_type=probability_type,
+            probability_parameters=probability_parameters,
+        )
+        out["K_NA"] += P.sum(1)
+        out["K_NB"][j0:j1] = P.sum(0)
+        out["K_NA_spatial"] += kns
+        out["K_NA_sigma2"] += kn2
+        out["PXB"] += P @ YB[j0:j1]
+        out["sigma2_related_num"] += float(s2r)
+        if keep_P:
+            blocks.append(P)
+    out["Sp"] = float(out["K_NA"].sum())
+    if keep_P:
+        out["P"] = np.concatenate(blocks, axis=1)
+    return out
+
+
 def dense_to_sparse_topk(mat, threshold):
     """utils.py:1369-1404 with sparse_method="topk", axis=0, descending=True (numpy backend: sort2 of the negated matrix,
     backend.py:1138-1142; COO assembly utils.py:1506-1510 with float column indices from ``nx.arange(type_as=mat)``)."""

@@ -1,4 +1,5 @@
-"""Micro-benchmark of the two E-step sweep kernels for every pipeline configuration (CUDA events, 100k x 100k pair)."""
+"""Micro-benchmark of the two E-step sweep kernels (CUDA events, 100k x 100k pair): pipeline shapes 0..2 and the
+diagnostic modes of sweep 2 (cfg 16 = bulk-copy pipeline alone, cfg 32 = arithmetic alone on a never-refilled ring)."""
 import argparse
 import ctypes as C
 import os
@@ -17,7 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--cells", type=int, default=100000)
 ap.add_argument("--genes", type=int, default=256)
 ap.add_argument("--reps", type=int, default=10)
-ap.add_argument("--cfgs", default="0,1,2")
+ap.add_argument("--cfgs", default="0,16,32", help="pipeline shape + 16 * diagnostic mode (1 = sweep 2 streams only, 2 = sweep 2 arithmetic only)")
 ap.add_argument("--warm-iters", type=int, default=3)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)

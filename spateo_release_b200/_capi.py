@@ -149,6 +149,10 @@ def load_library():
         "spb_voxel_accumulate": ([P, I32, I64, I32, P, I32, P, I32, P, I32, D, P, P, P, P, P, I64, I32, P, I64, P], C.c_int),
         "spb_inlier_from_nn": ([P, P, P, I64, I32, D, D, D, D, P, P, P, P, P], C.c_int),
         "spb_weighted_gram": ([P, I64, I64, I32, P, P, P, P, P], C.c_int),
+        "spb_gram_tc_scratch_floats": ([I32, I32, I64, C.POINTER(C.c_int64)], C.c_int),
+        "spb_gram_center": ([P, I64, I64, I32, P, P, P, P], C.c_int),
+        "spb_gram_prepare": ([P, I64, I64, I32, P, P, P, I64, I32, P, P, P, P], C.c_int),
+        "spb_gram_tc": ([P, P, P, P, I64, I64, I32, I32, P, P, P, I64, P, P, P], C.c_int),
         "spb_vfc_estep": ([P, I64, I64, I32, I32, P, P, D, D, D, D, D, P, P, P, P, P, P], C.c_int),
         "spb_field_eval_host": ([P, I64, I32, P, P, I32, D, P], C.c_int),
     }

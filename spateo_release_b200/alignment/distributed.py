@@ -28,6 +28,10 @@ def gather_transformations(local: dict, n_pairs: int, device=None) -> List[dict]
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     per_rank = (n_pairs + world - 1) // world
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        from .morpho_class import resolve_device  # GPU-index strings ("0") / None -> torch.device("cuda", i)
+
+        device = resolve_device(device)
     slab = torch.zeros((per_rank, 8), dtype=torch.float64, device=device)  # [pair index + 1, R00 R01 R10 R11, t0 t1, pad]
     for slot, p in enumerate(shard_pairs(n_pairs, rank, world)):
         tr = local[p]
@@ -73,8 +77,7 @@ def morpho_align_chain_sharded(
         if device is not None and pair_fn is pair_transformation:
             kw.setdefault("device", device)
         local[p] = pair_fn(models[p], models[p + 1], spatial_key=spatial_key, **kw)
-    gather_dev = device if (dist.is_initialized() and dist.get_backend() == "nccl") else None
-    transformation = gather_transformations(local, n_pairs, device=gather_dev)
+    transformation = gather_transformations(local, n_pairs, device=device if dist.is_initialized() and dist.get_backend() == "nccl" else None)
     models[0].obsm[key_added] = np.asarray(models[0].obsm[spatial_key]).copy()
     for i, (R, t) in enumerate(compose_transformations(transformation)):
         m = models[i + 1]

@@ -119,11 +119,17 @@ def morpho_align_transformation(
         Path(transformation_path).mkdir(parents=True, exist_ok=True)
         if not resume:
             remove_all_files_in_directory(transformation_path)
-        else:  # restart from the highest pair index that has a checkpoint (the reference recomputes that pair)
-            for i in range(n_pairs):
-                if os.path.exists(checkpoint(i)):
-                    first = i
-                    done.append(np.load(checkpoint(i), allow_pickle=True))
+        else:
+            # Restart at the highest pair index that has a checkpoint and recompute that pair, as the reference does
+            # (morpho_alignment.py:166-179) — but keep only the links BEFORE it, as plain dicts: the reference appends
+            # the re-computed pair on top of its own loaded copy (and its np.load lacks allow_pickle), which leaves
+            # len(models) entries and breaks morpho_align_apply_transformation.
+            have = [i for i in range(n_pairs) if os.path.exists(checkpoint(i))]
+            first = max(have) if have else 0
+            missing = [i for i in range(first) if i not in have]
+            if missing:
+                raise FileNotFoundError(f"resume: checkpoints of pairs {missing} are missing in {transformation_path}")
+            done = [_as_link(np.load(checkpoint(i), allow_pickle=True)) for i in range(first)]
     load = (lambda k: _read_h5ad(os.path.join(models_path, models[k]))) if from_disk else (lambda k: models[k])
     fixed = load(first)
     for i in range(first, n_pairs):
@@ -140,13 +146,18 @@ def morpho_align_transformation(
     return done
 
 
+def _as_link(tr) -> dict:
+    """A checkpoint loaded with ``np.load(..., allow_pickle=True)`` is a 0-d object array around the dict."""
+    return tr.item() if isinstance(tr, np.ndarray) and tr.dtype == object else tr
+
+
 def compose_transformations(transformation: List[dict]):
     """Serial prefix composition of per-pair similarities (morpho_alignment.py:274-301):
     ``cur_t = t_i @ cur_R.T + cur_t ; cur_R = cur_R @ R_i``. Returns the cumulative (R, t) of slices 1..n-1."""
     cur_R, cur_t = np.diag((1.0, 1.0)), np.zeros((2,))
     out = []
     for tr in transformation:
-        tr = tr.item() if isinstance(tr, np.ndarray) and tr.dtype == object else tr
+        tr = _as_link(tr)
         cur_t = tr["Translation"] @ cur_R.T + cur_t
         cur_R = cur_R @ tr["Rotation"]
         out.append((cur_R.copy(), cur_t.copy()))

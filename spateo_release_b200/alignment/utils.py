@@ -261,7 +261,7 @@ def inlier_from_NN(train_x, train_y, distance):
     return P, R, t, init_weight, sigma2, gamma
 
 
-def solve_RT_by_correspondence(X: np.ndarray, Y: np.ndarray, return_s: bool = False):
+def solve_RT_by_correspondence(X: np.ndarray, Y: np.ndarray, return_scale: bool = False):
     """spateo/alignment/utils.py:350-402 — least-squares R, t with X ~ Y R^T + t (no reflection guard, as there)."""
     tX, tY = np.mean(X, axis=0), np.mean(Y, axis=0)
     Xc, Yc = X - tX, Y - tY
@@ -269,7 +269,7 @@ def solve_RT_by_correspondence(X: np.ndarray, Y: np.ndarray, return_s: bool = Fa
     U, S, Vt = np.linalg.svd(H)
     R = Vt.T @ U.T
     t = np.mean(Xc, axis=0) - np.mean(Yc, axis=0) + tX - tY @ R.T
-    if return_s:
+    if return_scale:
         s = np.trace(Xc.T @ Xc - R.T @ (Yc.T @ Xc)) / np.trace(Yc.T @ Yc)
         return R, t, s
     return R, t

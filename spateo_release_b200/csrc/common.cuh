@@ -13,6 +13,14 @@
 extern "C" int64_t spb_launch_count(void);
 void spb_count_launch(int n = 1);
 
+// kernel attributes (dynamic shared-memory opt-in) are per device: index the "already set" flags by the current device
+#define SPB_MAX_DEVICES 64
+static inline int spb_current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < SPB_MAX_DEVICES) ? d : 0;
+}
+
 #define SPB_CHECK_LAUNCH()                      \
   do {                                          \
     cudaError_t e__ = cudaGetLastError();       \

@@ -20,12 +20,13 @@ namespace {
 constexpr int kRowTile = SPB_ROW_TILE;   // 1024 rows per CTA
 constexpr int kConsumers = SPB_THREADS;  // 256
 constexpr int kThreads = kConsumers + 32;
+constexpr int kColF4 = SPB_COLCONST_FLOATS / 4;  // float4 per column constant record (sweep 1 uses the first two)
 
 // Pipeline shape: kColStage columns per stage, kStages stages (compile-time variants, chosen by spb_set_sweep_config).
 template <int kColStage, int kStages>
 struct __align__(16) SmemLayoutT {
   float tile[kStages][kColStage][kRowTile];  // kColStage x 4 KB per stage
-  float4 cols[kStages][kColStage][4];        // per-column constants, pre-duplicated for packed math (64 B / column)
+  float4 cols[kStages][kColStage][kColF4];   // per-column constants, pre-duplicated for packed math (80 B / column)
   float red[2][kConsumers / 32][32];         // sweep-1 cross-warp staging
   uint64_t full[kStages];
   uint64_t empty[kStages];
@@ -227,6 +228,8 @@ __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStage
     const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
     const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
     const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
+    const ulonglong2 c3 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][3]);  // (c y0, c y0) (c y1, c y1)
+    const u64 cy2 = *reinterpret_cast<const u64*>(&sm.cols[s][jj][4]);               // (c y2, c y2)
     const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
     const u64 da = sqdist2(R.xa0, R.xa1, R.xa2, c0.x, c0.y, c1.x);
     const u64 db = sqdist2(R.xb0, R.xb1, R.xb2, c0.x, c0.y, c1.x);
@@ -241,19 +244,31 @@ __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStage
     A.sdb = fma2(tb, db, A.sdb);
     u64 wa = mul2(qa, g.x), wb = mul2(qb, g.y);
     if constexpr (kSparse) {
-      const float tau = sm.cols[s][jj][3].x;
+      const float tau = sm.cols[s][jj][4].z;
       wa = keep_ge(wa, tau);
       wb = keep_ge(wb, tau);
     }
-    const u64 pa = mul2(wa, c2.y), pb = mul2(wb, c2.y);
-    A.ka = add2(A.ka, pa);
-    A.kb = add2(A.kb, pb);
-    A.pxa = fma2(pa, c0.x, A.pxa);
-    A.pxb = fma2(pb, c0.x, A.pxb);
-    A.pya = fma2(pa, c0.y, A.pya);
-    A.pyb = fma2(pb, c0.y, A.pyb);
-    A.pza = fma2(pa, c1.x, A.pza);
-    A.pzb = fma2(pb, c1.x, A.pzb);
+    // P = w c and P y = w (c y): the column factor rides in the pre-multiplied constants (one packed op less per pair)
+    A.ka = fma2(wa, c2.y, A.ka);
+    A.kb = fma2(wb, c2.y, A.kb);
+    A.pxa = fma2(wa, c3.x, A.pxa);
+    A.pxb = fma2(wb, c3.x, A.pxb);
+    A.pya = fma2(wa, c3.y, A.pya);
+    A.pyb = fma2(wb, c3.y, A.pyb);
+    A.pza = fma2(wa, cy2, A.pza);
+    A.pzb = fma2(wb, cy2, A.pzb);
+  }
+}
+
+// diagnostic stages (spb_set_sweep_config debug modes): kDbg 1 = stream only (one add per GT value), used to measure the
+// bulk-copy pipeline alone; the full math on a never-refilled ring (kDbg 2) measures the arithmetic alone.
+template <int kColStage, int kStages>
+__device__ __forceinline__ void stream_only_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, S2Acc& A) {
+#pragma unroll
+  for (int jj = 0; jj < kColStage; ++jj) {
+    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+    A.ka = add2(A.ka, g.x);
+    A.kb = add2(A.kb, g.y);
   }
 }
 
@@ -342,18 +357,20 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
   const float* yg = colgeom + (int64_t)j * 8;  // (y0,y0,y1,y1,y2,y2,0,0)
   const float y0 = yg[0], y1 = yg[2], y2 = yg[4];
   const float af = (float)a, bf = (float)b, cf = (float)c;
-  float4* out = reinterpret_cast<float4*>(colconst + (int64_t)j * 16);
+  float4* out = reinterpret_cast<float4*>(colconst + (int64_t)j * SPB_COLCONST_FLOATS);
+  const float cy0 = cf * y0, cy1 = cf * y1, cy2 = cf * y2;
   out[0] = make_float4(y0, y0, y1, y1);
   out[1] = make_float4(y2, y2, af, af);
   out[2] = make_float4(bf, bf, cf, cf);
-  out[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  out[3] = make_float4(cy0, cy0, cy1, cy1);
+  out[4] = make_float4(cy2, cy2, 0.f, 0.f);  // [18..19] = tau (sparse mode top-k threshold), 0 = keep everything
   K_NB[j] = (float)(c * C[3]);                                // column sum of P (morpho_class.py:1176)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 2: row statistics
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kColStage, int kStages, int kMinBlocks, bool kSparse>
+template <int kColStage, int kStages, int kMinBlocks, bool kSparse, int kDbg = 0>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
@@ -365,7 +382,7 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
-  const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
+  ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
   const int32_t* list = collist + (int64_t)rb * nbb_pad;
   const int j_begin = cr.begin, j_end = cr.end;
   if (tid == 0) {
@@ -376,8 +393,10 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     fence_mbar_init();
   }
   __syncthreads();
+  const int nst = j_begin < j_end ? (j_end - j_begin + kColStage - 1) / kColStage : 0;
   if (warp == kConsumers / 32) {
-    if (j_begin < j_end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, list, colconst, 16, i0, cr, NBb, lane);
+    if constexpr (kDbg == 2) cr.end = min(cr.end, cr.begin + kStages * kColStage);  // fill the ring once, never refill
+    if (j_begin < j_end) producer_loop<kColStage, kStages>(sm, GT, ldx, col_index, list, colconst, SPB_COLCONST_FLOATS, i0, cr, NBb, lane);
     return;
   }
   const u64 CQ = pk(sc->c_q, sc->c_q), CS = pk(sc->c_s, sc->c_s);
@@ -385,13 +404,15 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const RowRegs R = load_rows(XA, ldx, lm, nullptr, r);
   S2Acc A;
   A.clear();
-  const int nst = j_begin < j_end ? (j_end - j_begin + kColStage - 1) / kColStage : 0;
   for (int st = 0; st < nst; ++st) {
     const int s = st % kStages;
-    mbar_wait(&sm.full[s], (st / kStages) & 1);
-    sweep2_stage<kColStage, kStages, kSparse>(sm, s, tid, R, CQ, CS, A);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.empty[s]);
+    if (kDbg != 2 || st < kStages) mbar_wait(&sm.full[s], (st / kStages) & 1);
+    if constexpr (kDbg == 1) stream_only_stage<kColStage, kStages>(sm, s, tid, A);
+    else sweep2_stage<kColStage, kStages, kSparse>(sm, s, tid, R, CQ, CS, A);
+    if constexpr (kDbg != 2) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[s]);
+    }
   }
   A.store(rowpart + ((int64_t)seg * 8) * ldx + r, ldx);
 }
@@ -561,7 +582,7 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
     float p = 0.f;
     if (j < NBb && i < NA) {
       const int64_t row = col_index ? col_index[j] : j;
-      const float* cc = colconst + (int64_t)j * 16;
+      const float* cc = colconst + (int64_t)j * SPB_COLCONST_FLOATS;
       const float4 ya = make_float4(cc[0], cc[2], cc[4], 0.f);
       const float cj = cc[10];
       const float d = sqdist(XA[i], XA[ldx + i], XA[2 * ldx + i], ya);
@@ -584,7 +605,7 @@ __global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, 
 // row is contiguous) and finds the k-th largest w EXACTLY by a 3-level radix select on the float bits (12 + 12 + 7 bits;
 // w >= 0 so the bit pattern is monotone). After the first level the surviving candidates are gathered into shared
 // memory, so the column is normally read twice; that second read also sums the mass above the selected bin:
-//   tau_j   -> colconst[j][12..13]  (sweep 2 keeps pairs with w >= tau_j; exact ties at tau_j are all kept)
+//   tau_j   -> colconst[j][18..19]  (sweep 2 keeps pairs with w >= tau_j; exact ties at tau_j are all kept)
 //   K_NB_j  = c_j * sum_{w >= tau_j} w
 // The weight is evaluated with the same instruction sequence as the packed sweep (sub, mul, fma, fma, fma, ex2, mul), so
 // both kernels see bit-identical w.
@@ -656,7 +677,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   __shared__ SelShared sh;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int jb = blockIdx.x;
-  float* cc = colconst + (int64_t)jb * 16;
+  float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
   const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   const float* g = GT + row * ldx;
@@ -788,8 +809,8 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
     }
   }
   if (tid == 0) {
-    cc[12] = tau;
-    cc[13] = tau;
+    cc[18] = tau;
+    cc[19] = tau;
     K_NB[jb] = cj * kept;
   }
 }
@@ -804,8 +825,8 @@ col_emit_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __rest
                 float* __restrict__ vals) {
   __shared__ int cnt;
   const int jb = blockIdx.x, tid = threadIdx.x;
-  const float* cc = colconst + (int64_t)jb * 16;
-  const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10], tau = cc[12];
+  const float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
+  const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10], tau = cc[18];
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   const float* g = GT + row * ldx;
   const float cq = sc->c_q;
@@ -867,7 +888,7 @@ col_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
                   const spb_scalars* __restrict__ sc, int NA, unsigned long long* __restrict__ colbest) {
   __shared__ unsigned long long red[kSelThreads / 32];
   const int jb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const float* cc = colconst + (int64_t)jb * 16;
+  const float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
   const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   unsigned long long best = 0ull;
@@ -900,28 +921,30 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   const float x0 = XA[i], x1 = XA[ldx + i], x2 = XA[2 * ldx + i], li = lm[i], cq = sc->c_q;
   unsigned long long best = 0ull;
   for (int j = j0; j < j1; ++j) {
-    const float4 c0 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * 16);
-    const float4 c1 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * 16 + 4);
-    const float cj = colconst[(int64_t)j * 16 + 10];
+    const float4 c0 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * SPB_COLCONST_FLOATS);
+    const float4 c1 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * SPB_COLCONST_FLOATS + 4);
+    const float cj = colconst[(int64_t)j * SPB_COLCONST_FLOATS + 10];
     const int64_t row = col_index ? (int64_t)col_index[j] : (int64_t)j;
     float w = pair_weight(x0, x1, x2, c0.x, c0.z, c1.x, cq, li, GT[row * ldx + i]);
-    w = w >= colconst[(int64_t)j * 16 + 12] ? w : 0.f;  // sparse mode: entries below the column's top-k are absent
+    w = w >= colconst[(int64_t)j * SPB_COLCONST_FLOATS + 18] ? w : 0.f;  // sparse mode: entries below the column's top-k are absent
     const unsigned long long key = argmax_key(w * cj, j);
     best = key > best ? key : best;
   }
   if (j0 < j1) atomicMax(rowbest + i, best);
 }
 
+int g_sweep_dbg = 0;  // 0 product, 1 stream-only sweep 2, 2 arithmetic-only sweep 2 (diagnostics, spb_set_sweep_config(16 * mode + cfg))
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
 template <int C, int S, int B>
 int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid(p->ldx / kRowTile, p->seg1);
   estep_sweep1_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
@@ -929,17 +952,18 @@ int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   return 0;
 }
 
-template <int C, int S, int B, bool SP>
+template <int C, int S, int B, bool SP, int DBG = 0>
 int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   dim3 grid(p->ldx / kRowTile, p->seg2);
-  estep_sweep2_kernel<C, S, B, SP><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
+  estep_sweep2_kernel<C, S, B, SP, DBG><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
                                                                   p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
@@ -957,8 +981,10 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
 }
 
 extern "C" int spb_set_sweep_config(int32_t cfg) {
-  if (cfg < 0 || cfg > 2) return SPB_EINVAL;
-  g_sweep_cfg = cfg;
+  const int shape = cfg & 15, dbg = (cfg >> 4) & 15;
+  if (cfg < 0 || shape > 2 || dbg > 2) return SPB_EINVAL;
+  g_sweep_cfg = shape;
+  g_sweep_dbg = dbg;
   return 0;
 }
 
@@ -1002,6 +1028,8 @@ extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
   if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_dbg == 1) rc = launch_sweep2<8, 3, 2, false, 1>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_dbg == 2) rc = launch_sweep2<8, 3, 2, false, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep2<8, 3, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
@@ -1014,11 +1042,12 @@ extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stre
 extern "C" int spb_estep_col_select(const spb_em_params* p, int32_t iter, void* stream) {
   if (p->sparse_k <= 0) return SPB_EINVAL;
   const size_t smem = sizeof(uint32_t) * kSelBins + sizeof(float) * kSelBins + sizeof(float) * kSelCap;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(col_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   col_select_kernel<<<p->NBb, kSelThreads, smem, (cudaStream_t)stream>>>(p->GT, p->ldx, batch_ptr(p, iter), p->colconst,
                                                                       p->XAHat, p->lm, p->sc, p->NA, p->sparse_k, p->K_NB,

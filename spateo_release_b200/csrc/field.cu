@@ -204,11 +204,12 @@ extern "C" int spb_field_eval(const double* q, int64_t n, int32_t D, const doubl
   if (D < 1 || D > 3) return SPB_EINVAL;
   const size_t smem = sizeof(double) * 2 * (size_t)K * D;
   if (smem > 96 * 1024) return SPB_EUNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(field_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   field_eval_kernel<<<(unsigned)((n + 127) / 128), 128, smem, ST>>>(q, n, D, z, Coff, K, beta, out);
   SPB_CHECK_LAUNCH();
@@ -225,13 +226,14 @@ extern "C" int spb_field_geometry(const spb_field_desc* f, const double* X, int6
   if (torsion != nullptr && f->D != 3) return SPB_EINVAL;
   const size_t smem = sizeof(double) * 2 * (size_t)f->K * f->D;
   if (smem > 96 * 1024) return SPB_EUNSUPPORTED;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(field_geometry_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(field_geometry_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   GeomOut o{V, J, acc, acc_mat, curv, curv_mat, curl, torsion, div, det};
   const unsigned grid = (unsigned)((n + 127) / 128);

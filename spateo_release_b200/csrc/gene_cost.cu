@@ -320,11 +320,12 @@ extern "C" int spb_gene_cost(const float* A, int64_t lda, const float* rowtermA,
   const float neg_inv2b = prob_type == SPB_PROB_GAUSS ? -1.0f / (2.0f * prob_param) : 0.f;
   dim3 grid((unsigned)(ldx / BM), (unsigned)((NB + BN - 1) / BN));
   const size_t dyn = 32 * 256 * sizeof(unsigned long long);  // second-level accumulators
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(gene_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   gene_cost_kernel<<<grid, 256, dyn, ST>>>(A, lda, rowtermA, B, ldb, rowtermB, NA, NB, Gp, metric, prob_type, neg_inv2b,
                                          accumulate, GT, ldx);

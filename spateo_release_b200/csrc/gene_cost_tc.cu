@@ -317,14 +317,16 @@ extern "C" int spb_gene_cost_tc(const float* A_hi, const float* A_lo, int64_t ld
   if ((rc = make_map(&mb_lo, B_lo, NB, Gp, ldb, TM))) return rc;
   const int tiles_i = (int)((ldx + TN - 1) / TN), tiles_j = (int)((NB + TM - 1) / TM);
   const float neg_inv2b = prob_type == SPB_PROB_GAUSS ? -1.0f / (2.0f * prob_param) : 0.f;
-  static int n_sm = 0;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  static int n_sm_dev[SPB_MAX_DEVICES] = {};  // SM count + shared-memory opt-in, per device
+  const int dev_ = spb_current_device();
+  if (n_sm_dev[dev_] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev_);
     cudaError_t e = cudaFuncSetAttribute(gene_cost_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem) + 1024);
     if (e != cudaSuccess) return (int)e;
+    n_sm_dev[dev_] = n;
   }
+  const int n_sm = n_sm_dev[dev_];
   const int grid = min(n_sm, tiles_i * tiles_j);
   gene_cost_tc_kernel<<<grid, kTcThreads, sizeof(TcSmem) + 1024, ST>>>(ma_hi, ma_lo, mb_hi, mb_lo, rowtermA, rowtermB, NA, NB,
                                                                         (int)(Gp / TK), tiles_i, tiles_j, metric, prob_type,

@@ -158,6 +158,64 @@ weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, co
   }
 }
 
+// Small inducing sets (K <= 32): every thread owns a few of the K x (K + 3) entries, rows are staged through shared memory
+// in chunks of 128, fp64 products and accumulation as in weighted_gram_kernel (same numerics, ~10x less time at K = 15).
+constexpr int kSmallK = 32;
+__global__ void __launch_bounds__(256)
+gram_small_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const float* __restrict__ w,
+                  const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX, int rows_per_block) {
+  constexpr int kChunk = 128, kPitch = kChunk + 1;
+  __shared__ float As[kSmallK][kPitch];
+  __shared__ float Bs[kSmallK + 3][kPitch];
+  const int KB = K + 3, nent = K * KB;
+  constexpr int kPer = (kSmallK * (kSmallK + 3) + 255) / 256;  // 5 entries per thread at most
+  double acc[kPer];
+  int ek[kPer], el[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int e = threadIdx.x + q * 256;
+    acc[q] = 0.0;
+    ek[q] = e < nent ? e / KB : -1;
+    el[q] = e < nent ? e % KB : 0;
+  }
+  const int r_begin = blockIdx.x * rows_per_block, r_end = min(N, r_begin + rows_per_block);
+  for (int r0 = r_begin; r0 < r_end; r0 += kChunk) {
+    const int nr = min(kChunk, r_end - r0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < KB * kChunk; q += 256) {
+      const int row = q / kChunk, rr = q % kChunk;
+      const bool ok = rr < nr;
+      float a = 0.f, b = 0.f;
+      if (ok) {
+        if (row < K) {
+          a = UT[(int64_t)row * ldx + r0 + rr];
+          b = a * w[r0 + rr];
+        } else {
+          b = X3[(int64_t)(row - K) * ldx + r0 + rr];
+        }
+      }
+      if (row < K) As[row][rr] = a;
+      Bs[row][rr] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      if (ek[q] < 0) continue;
+      const float* ar = As[ek[q]];
+      const float* br = Bs[el[q]];
+      double s = 0.0;
+      for (int rr = 0; rr < kChunk; ++rr) s += (double)ar[rr] * (double)br[rr];
+      acc[q] += s;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    if (ek[q] < 0) continue;
+    if (el[q] < K) atomicAdd(&UtWU[(int64_t)ek[q] * K + el[q]], acc[q]);
+    else atomicAdd(&UtX[ek[q] * 3 + (el[q] - K)], acc[q]);
+  }
+}
+
 // SparseVFC E-step (dynamo scVectorField.SparseVFC get_P + bookkeeping; SURVEY.md Appendix E — parity unpinned):
 //   V_i = U_i C, r_i = |Y_i - V_i|^2, P_i = t1 / (t1 + t2), t1 = exp(-r / 2 sigma2), then the clamp to minP.
 // sums: [0] sum P_pre r  [1] sum P_pre  [2] sum P r  [3] sum P  [4] #{P > theta}
@@ -645,6 +703,21 @@ extern "C" int spb_update_gamma_alpha(const spb_em_params* p, void* stream) {
 extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
   pxb_term_kernel<<<(p->NA + 255) / 256, 256, 0, ST>>>(*p);
   SPB_CHECK_LAUNCH();
+  if (p->UT_hi != nullptr) {  // tensor-core contraction (tcgen05, 3xTF32): every K the caller prepared operands for
+    int rc = spb_gram_prepare(p->UT, p->ldx, p->NA, p->K, p->UT_mean, p->K_NA, p->PXB_term, p->ldx, 3, p->GB_hi, p->GB_lo,
+                              p->gram_sums, stream);
+    if (rc) return rc;
+    return spb_gram_tc(p->UT_hi, p->UT_lo, p->GB_hi, p->GB_lo, p->ldx, p->NA, p->K, 3, p->UT_mean, p->gram_sums,
+                       p->gram_scratch, p->gram_scratch_floats, p->UtWU, p->UtPXB, stream);
+  }
+  if (p->K <= kSmallK) {
+    int rows = (p->NA + 295) / 296;
+    rows = ((rows + 127) / 128) * 128;
+    gram_small_kernel<<<(p->NA + rows - 1) / rows, 256, 0, ST>>>(p->UT, p->ldx, p->NA, p->K, p->K_NA, p->PXB_term, p->UtWU,
+                                                                 p->UtPXB, rows);
+    SPB_CHECK_LAUNCH();
+    return 0;
+  }
   const int ntile = (p->K + 31) / 32;
   const int npairs = ntile * (ntile + 1) / 2;
   const int rows_per_block = gram_rows_per_block(p->NA, npairs);
@@ -660,6 +733,13 @@ extern "C" int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_
   if (e != cudaSuccess) return (int)e;
   e = cudaMemsetAsync(UtX, 0, sizeof(double) * (size_t)K * 3, ST);
   if (e != cudaSuccess) return (int)e;
+  if (K <= kSmallK) {
+    int rows = (int)((N + 295) / 296);
+    rows = ((rows + 127) / 128) * 128;
+    gram_small_kernel<<<(unsigned)((N + rows - 1) / rows), 256, 0, ST>>>(UT, ldx, (int)N, K, w, X3, UtWU, UtX, rows);
+    SPB_CHECK_LAUNCH();
+    return 0;
+  }
   const int ntile = (K + 31) / 32;
   const int npairs = ntile * (ntile + 1) / 2;
   const int rows_per_block = gram_rows_per_block(N, npairs);
@@ -692,11 +772,12 @@ extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
   if (p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
   const int Kp = (p->K + 1) & ~1;
   const size_t smem = sizeof(double) * (2 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(nonrigid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev_] = true;
   }
   nonrigid_solve_kernel<<<1, 256, smem, ST>>>(*p);
   SPB_CHECK_LAUNCH();

@@ -158,10 +158,11 @@ def SparseVFC(
             it += 1
         C = Cd[:, :D].cpu().numpy()
         # final field on the cells and on the grid
+        # scratch outputs of the final evaluation are bound to names so they outlive the (asynchronous) launch
+        P_scratch, Pf_scratch, PY3_scratch = sums.new_empty(ldn), torch.empty_like(Pf), torch.empty_like(PY3)
         check(
             lib.spb_vfc_estep(ptr(UT), ldn, N, M, D, ptr(Cd), ptr(Yd), max(sigma2, 1e-300), gamma, float(a), float(minP),
-                              float(theta), ptr(sums.new_empty(ldn)), ptr(V), ptr(torch.empty_like(Pf)),
-                              ptr(torch.empty_like(PY3)), ptr(sums), st),
+                              float(theta), ptr(P_scratch), ptr(V), ptr(Pf_scratch), ptr(PY3_scratch), ptr(sums), st),
             "spb_vfc_estep(final)",
         )
         V_host = V.cpu().numpy()

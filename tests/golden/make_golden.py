@@ -39,6 +39,13 @@ CASES = {
                              kw=dict(sparse_calculation_mode=True, sparse_top_k=48)),
     "3d_svi_sparse32": dict(n_a=1250, n_b=1200, g=20, dim=3, svi=True, max_iter=110, K=15, warp=0.0,
                             kw=dict(sparse_calculation_mode=True, sparse_top_k=32)),
+    # BASELINE configs[0]: 2-D, 5000 x 5000 cells, 100 genes, 200 iterations, the reference's default
+    # SVI mode (batch 1000) and the full EM; E-step dumps at iterations 0 / 60 / 150 (5 row blocks of 1024 moving cells,
+    # several column segments, zero-tile culling active at 150)
+    "c1_2d_svi": dict(n_a=5000, n_b=5000, g=100, dim=2, svi=True, max_iter=200, K=15, warp=0.0, kw={},
+                      dump_iters=(0, 60, 150)),
+    "c1_2d_full_warp": dict(n_a=5000, n_b=5000, g=100, dim=2, svi=False, max_iter=200, K=15, warp=2.0, kw={},
+                            dump_iters=(0, 60, 150)),
 }
 DUMP_ITERS = (0, 3, 60, 95, 110)
 P_DUMP_ITERS = (0, 95)
@@ -96,6 +103,7 @@ def run_reference(cfg, dtype, dump):
     if dump and cfg.get("dump_exp_dist"):
         out["exp_dist"] = np.asarray(ref.exp_layer_dist[0])
     traj = {k: [] for k in ("sigma2", "gamma", "Sp", "Sp_spatial", "Sp_sigma2", "sigma2_variance")}
+    DUMP_ITERS = cfg.get("dump_iters", globals()["DUMP_ITERS"])
     for it in range(ref.max_iter):
         if ref.SVI_mode:
             ref._update_batch(iter=it)

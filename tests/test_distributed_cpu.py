@@ -83,3 +83,37 @@ def test_gather_single_process():
     assert np.allclose(out[0]["Rotation"], _rot(0.3)) and np.allclose(out[1]["Translation"], 0)
     (R1, t1), (R2, t2) = compose_transformations(out)
     assert np.allclose(R2, _rot(0.3) @ _rot(-0.1))
+
+
+def test_transformation_resume_recomputes_only_the_last_checkpointed_pair(tmp_path, monkeypatch):
+    """``resume=True`` (morpho_alignment.py:166-179): restart at the highest checkpointed pair, return exactly
+    len(models) - 1 plain dicts equal to an uninterrupted run, and feed morpho_align_apply_transformation unchanged."""
+    from spateo_release_b200.alignment import morpho_alignment as ma
+
+    calls = []
+
+    def counting_pair(modelA, modelB, spatial_key="spatial", **kw):
+        calls.append((modelA.uns["pose"], modelB.uns["pose"]))
+        return _fake_pair(modelA, modelB, spatial_key=spatial_key)
+
+    monkeypatch.setattr(ma, "pair_transformation", counting_pair)
+    models = _models(5)
+    path = str(tmp_path / "tr")
+    full = ma.morpho_align_transformation(models, save_transformation=True, transformation_path=path, verbose=False)
+    assert len(full) == 4 and len(calls) == 4
+    os.remove(os.path.join(path, "transformation_3.npy"))  # an interrupted run: pairs 0..2 are on disk
+    calls.clear()
+    resumed = ma.morpho_align_transformation(models, save_transformation=True, transformation_path=path, resume=True,
+                                             verbose=False)
+    assert len(resumed) == 4 and all(isinstance(t, dict) for t in resumed)
+    assert len(calls) == 2, "pairs 2 (highest checkpoint, recomputed like the reference) and 3 only"
+    for a, b in zip(full, resumed):
+        assert np.allclose(a["Rotation"], b["Rotation"]) and np.allclose(a["Translation"], b["Translation"])
+    assert sorted(os.listdir(path)) == [f"transformation_{i}.npy" for i in range(4)]
+    placed = ma.morpho_align_apply_transformation(_models(5), transformation=resumed, verbose=False)
+    ref = np.asarray(placed[0].obsm["align_spatial"])
+    for m in placed[1:]:
+        assert np.abs(np.asarray(m.obsm["align_spatial"]) - ref).max() < 1e-9
+    # and from the checkpoints on disk (np.load(..., allow_pickle=True) objects)
+    placed2 = ma.morpho_align_apply_transformation(_models(5), transformation=None, transformation_path=path, verbose=False)
+    assert np.abs(np.asarray(placed2[4].obsm["align_spatial"]) - ref).max() < 1e-9

@@ -6,7 +6,6 @@ reference with the reference's own fp32-vs-fp64 deviation printed beside it (the
 from its fp64 twin after 100+ iterations — SURVEY.md Appendix F).
 """
 
-import ast
 import ctypes as C
 
 import numpy as np
@@ -17,44 +16,12 @@ pytestmark = pytest.mark.gpu
 from oracle import morpho_oracle as mo  # noqa: E402
 
 
-def _adata_from_golden(g):
-    import pandas as pd
-
-    from spateo_release_b200.anndata_lite import AnnDataLite
-
-    G = g["exp_moving"].shape[1]
-    var = pd.DataFrame(index=[f"g{i}" for i in range(G)])
-    mov = AnnDataLite(g["exp_moving"], var=var.copy(), obsm={"spatial": g["raw_coords_moving"]})
-    fix = AnnDataLite(g["exp_fixed"], var=var.copy(), obsm={"spatial": g["raw_coords_fixed"]})
-    return mov, fix
-
-
-def _cfg(g):
-    return ast.literal_eval(str(g["cfg"]))
-
-
-def _model(g, **over):
-    import spateo_release_b200 as st
-
-    cfg = _cfg(g)
-    mov, fix = _adata_from_golden(g)
-    kw = dict(SVI_mode=cfg["svi"], max_iter=cfg["max_iter"], K=cfg["K"], verbose=False, device="0", vecfld_key_added="vf")
-    kw.update(cfg["kw"])
-    if "guide_fixed" in g:
-        kw["guidance_pair"] = [g["guide_fixed"], g["guide_moving"]]
-    kw.update(over)
-    np.random.seed(0)
-    return st.align.Morpho_pairwise(sampleA=mov, sampleB=fix, **kw)
-
-
-def _relF(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
-
-
-def _relmax(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+from parity_helpers import adata_from_golden as _adata_from_golden  # noqa: E402
+from parity_helpers import cfg_of as _cfg  # noqa: E402
+from parity_helpers import model_from_golden as _model  # noqa: E402
+from parity_helpers import poke_golden_estep as _poke_estep_state  # noqa: E402
+from parity_helpers import relF as _relF  # noqa: E402
+from parity_helpers import relmax as _relmax  # noqa: E402
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -130,33 +97,6 @@ def test_gene_cost_other_metrics(metric):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def _poke_estep_state(m, g, it, sfx=""):
-    """Overwrite the device state with the reference's E-step inputs at iteration ``it``."""
-    import torch
-
-    from spateo_release_b200._capi import SpbScalars
-
-    s, NA, D = m._state, m.NA, m.D
-    dev = m._dev
-    XAHat = g[f"it{it}_in_XAHat{sfx}"].astype(np.float32)
-    alpha = g[f"it{it}_in_alpha{sfx}"].astype(np.float64)
-    SigmaDiag = g[f"it{it}_in_SigmaDiag{sfx}"].astype(np.float64)
-    sigma2 = float(g[f"it{it}_in_sigma2{sfx}"])
-    XAHat, alpha, SigmaDiag = m._sorted(XAHat), m._sorted(alpha), m._sorted(SigmaDiag)  # device rows are in processing order
-    s["XAHat"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(XAHat.T)).to(dev)
-    s["alpha"][:NA] = torch.from_numpy(alpha.astype(np.float32)).to(dev)
-    s["SigmaDiag"][:NA] = torch.from_numpy(SigmaDiag.astype(np.float32)).to(dev)
-    mmv = alpha * np.exp(-SigmaDiag / sigma2)
-    s["mm"][:NA] = torch.from_numpy(mmv.astype(np.float32)).to(dev)
-    s["lm"][:NA] = torch.from_numpy(np.log2(mmv).astype(np.float32)).to(dev)
-    s["xb4"][:, :D] = torch.from_numpy(g["pre_coordsB" + sfx].astype(np.float32)).to(dev)
-    sc = m._read_scalars()
-    sc.sigma2, sc.gamma = sigma2, float(g[f"it{it}_in_gamma{sfx}"])
-    sc.sigma2_variance = float(g[f"it{it}_in_sigma2_variance{sfx}"])
-    s["sc"].copy_(torch.from_numpy(np.frombuffer(bytes(sc), dtype=np.uint8).copy()))
-    m._params.samples_s = float(g["pre_samples_s" + sfx])
-
-
 @pytest.mark.parametrize("case", ["2d_full", "3d_full_warp"])
 @pytest.mark.parametrize("it", [0, 95])
 def test_single_estep_matches_float64_oracle(golden, case, it):
@@ -291,7 +231,8 @@ def test_sparse_mode_edge_cases():
 
 
 @pytest.mark.parametrize("case", ["2d_full", "3d_full_warp", "2d_full_nonn_euc", "3d_svi", "2d_full_guide_both",
-                                  "2d_svi_guide_nonrigid", "2d_full_sparse48", "3d_svi_sparse32"])
+                                  "2d_svi_guide_nonrigid", "2d_full_sparse48", "3d_svi_sparse32", "c1_2d_svi",
+                                  "c1_2d_full_warp"])
 def test_full_run_matches_reference(golden, case):
     """Whole alignment through the public class: aligned coordinates within 1e-3 (relative to the coordinate range)
     of BOTH the float32 and the float64 reference runs; sigma2 / gamma close; P against the float64 reference."""

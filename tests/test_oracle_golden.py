@@ -131,3 +131,66 @@ def test_ba_transform_matches_reference_fixture(golden, tag):
             sfx = f"{dt}_{ds}"
             assert np.array_equal(X, g[f"{tag}_XAHat_{sfx}"]) and X.dtype == g[f"{tag}_XAHat_{sfx}"].dtype
             assert np.array_equal(V, g[f"{tag}_vel_{sfx}"]) and np.array_equal(O, g[f"{tag}_opt_{sfx}"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0] scale (5000 x 5000 cells, 100 genes, 2-D): preparation + E-step dumps of the reference
+# ---------------------------------------------------------------------------------------------------------------------
+C1_CASES = ["c1_2d_svi", "c1_2d_full_warp"]
+
+
+@pytest.mark.parametrize("case", C1_CASES)
+def test_config1_preparation_matches_reference(golden, case):
+    g = golden(case)
+    orc = _make_oracle(g, "float32")
+    orc.prepare()
+    assert _relmax(orc.U, g["pre_U"]) < 1e-5
+    assert _relmax(orc.coordsA, g["pre_coordsA"]) < 1e-4
+    assert _relmax(orc.sigma2, g["pre_sigma2_0"]) < 1e-4
+    assert _relmax(orc.probability_parameters[0], g["pre_beta2"]) < 1e-4
+    assert orc.inlier_P.shape == g["pre_inlier_P"].shape and _relmax(orc.init_R, g["pre_init_R"]) < 1e-4
+    if orc.SVI_mode:
+        assert np.array_equal(orc.batch_perm, g["pre_batch_perm"])
+
+
+@pytest.mark.parametrize("case", C1_CASES)
+@pytest.mark.parametrize("it", [0, 150])
+def test_config1_estep_matches_reference_dump(golden, case, it):
+    """float32 oracle E-step (evaluated in column chunks) on the reference's inputs against the reference's outputs."""
+    g = golden(case)
+    XAHat, alpha, SD = g[f"it{it}_in_XAHat"], g[f"it{it}_in_alpha"], g[f"it{it}_in_SigmaDiag"]
+    sigma2, gamma = g[f"it{it}_in_sigma2"], g[f"it{it}_in_gamma"]
+    yb, eB = g["pre_coordsB"], g["exp_fixed"]
+    if f"it{it}_in_batch_idx" in g:
+        yb, eB = yb[g[f"it{it}_in_batch_idx"]], eB[g[f"it{it}_in_batch_idx"]]
+    out = mo.estep_column_chunks(
+        Dim=np.float32(yb.shape[1]), XAHat=XAHat, YB=yb, exp_A=[g["exp_moving"]], exp_B=[eB], metric=["kl"], sigma2=sigma2,
+        model_mul=(alpha * np.exp(-SD / sigma2))[:, None], gamma=gamma, samples_s=g["pre_samples_s"],
+        sigma2_variance=np.float32(g[f"it{it}_in_sigma2_variance"]), probability_type=["gauss"],
+        probability_parameters=[g["pre_beta2"]], chunk=1250,
+    )
+    # chunked accumulation changes the fp32 summation order of the row statistics: tolerance = fp32 noise
+    assert _relmax(out["K_NB"], g[f"it{it}_out_K_NB"]) < 1e-4
+    assert _relmax(out["K_NA"], g[f"it{it}_out_K_NA"]) < 5e-4
+    assert _relmax(out["K_NA_spatial"], g[f"it{it}_out_K_NA_spatial"]) < 5e-4
+    assert _relmax(out["K_NA_sigma2"], g[f"it{it}_out_K_NA_sigma2"]) < 5e-4
+    assert _relmax(out["PXB"], g[f"it{it}_out_PXB"]) < 5e-4
+
+
+def test_estep_column_chunks_equals_one_block(golden):
+    """The chunked evaluation is the same computation as one get_P_core call over all columns."""
+    g = golden("3d_full_warp")
+    it = 95
+    f8 = lambda k: g[k].astype(np.float64)
+    XAHat, alpha, SD = f8(f"it{it}_in_XAHat"), f8(f"it{it}_in_alpha"), f8(f"it{it}_in_SigmaDiag")
+    sigma2, gamma = float(g[f"it{it}_in_sigma2"]), float(g[f"it{it}_in_gamma"])
+    yb = f8("pre_coordsB")
+    common = dict(sigma2=sigma2, model_mul=(alpha * np.exp(-SD / sigma2))[:, None], gamma=gamma,
+                  samples_s=float(g["pre_samples_s"]), sigma2_variance=float(g[f"it{it}_in_sigma2_variance"]),
+                  probability_type=["gauss"], probability_parameters=[float(g["pre_beta2"])])
+    out = mo.estep_column_chunks(Dim=3.0, XAHat=XAHat, YB=yb, exp_A=[f8("exp_moving")], exp_B=[f8("exp_fixed")],
+                                 metric=["kl"], chunk=77, keep_P=True, **common)
+    [ed] = mo.calc_distance(f8("exp_moving"), f8("exp_fixed"), "kl")
+    P, kns, kn2, s2r = mo.get_P_core(Dim=3.0, spatial_dist=mo.euc_distance(XAHat, yb), exp_dist=[ed], **common)
+    assert _relmax(out["P"], P) < 1e-12 and _relmax(out["K_NA_spatial"], kns) < 1e-12
+    assert _relmax(out["K_NA_sigma2"], kn2) < 1e-12 and abs(out["sigma2_related_num"] - s2r) < 1e-12 * abs(s2r)
