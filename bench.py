@@ -424,11 +424,14 @@ def main():
 
     # ---- device-resident arms: EM loop only, cost matrix in HBM ----
     # (1) product default: exact zero-tile culling on; (2) dense sweeps (culling off) for the plain 8 B/pair roofline
-    def timed_arm(cull, n_warm, n_steps, sample_clocks):
+    def timed_arm(cull, n_warm, n_steps, sample_clocks, events=False):
+        """events=False: the product path (iterations replayed from CUDA graphs) -> step times; events=True: the same launch
+        sequence enqueued kernel by kernel with CUDA events around the two sweeps of every iteration -> roofline."""
         m.cull_zero_tiles = cull
         sampler = ClockSampler(local_rank)
         step_ms, sweep_ms, visited = [], [], []
         launches0 = 0
+        replayed0 = 0
         for s in range(n_warm + n_steps):
             m.reset_state()
             ev = []
@@ -437,10 +440,11 @@ def main():
                 if sample_clocks:
                     sampler.start()
                 launches0 = lib.spb_launch_count()
+                replayed0 = getattr(m, "graph_replayed_launches", 0)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            m.run_em(sweep_events=ev)
+            m.run_em(sweep_events=ev if events else None)
             consensus_step()
             e1.record()
             barrier()
@@ -448,13 +452,16 @@ def main():
                 step_ms.append(max_over_ranks(e0.elapsed_time(e1)))
                 sweep_ms.append([(a.elapsed_time(b), c.elapsed_time(d)) for (a, b, c, d) in ev])
                 visited.append(m._state["trace_buf"][:, 7].cpu().numpy().copy())
-        launches = lib.spb_launch_count() - launches0
+        # kernels enqueued directly + kernels inside replayed CUDA graphs (counted per captured graph x replays)
+        launches = (lib.spb_launch_count() - launches0) + (getattr(m, "graph_replayed_launches", 0) - replayed0)
         clocks = sampler.stop() if sample_clocks else None
         return dict(ms=float(np.mean(step_ms)), sweeps=np.array(sweep_ms, dtype=np.float64), visited=np.array(visited),
                     launches=int(launches), clocks=clocks)
 
     main_arm = timed_arm(True, args.warmup, args.steps, True)
+    main_ev = timed_arm(True, 0, max(1, min(args.steps, 2)), False, events=True)   # per-launch sweep timings, same workload
     dense_arm = timed_arm(False, min(args.warmup, 1), max(1, min(args.steps, 2)), False)
+    dense_ev = timed_arm(False, 0, 1, False, events=True)
     m.cull_zero_tiles = True
     ms_per_step = main_arm["ms"]
     launches, clocks = main_arm["launches"], main_arm["clocks"]
@@ -472,14 +479,14 @@ def main():
     tiles_all = float(nrb) * cols
     # algorithmic bytes of one sweep launch = 4 B x (cell pairs the launch has to read): all pairs when dense, the visited
     # (row block x column) tiles x N_A/nrb rows when culling skipped the provably-zero tiles
-    sw = main_arm["sweeps"]                                     # [steps, iters, 2] ms
-    vis = main_arm["visited"]                                   # [steps, iters] tiles
+    sw = main_ev["sweeps"]                                      # [steps, iters, 2] ms
+    vis = main_ev["visited"]                                    # [steps, iters] tiles
     bytes_per_launch = 4.0 * vis * (float(NA) / nrb)            # [steps, iters]
     s1_gbs = float(bytes_per_launch.sum() / (sw[..., 0].sum() * 1e-3) / 1e9)
     s2_gbs = float(bytes_per_launch.sum() / (sw[..., 1].sum() * 1e-3) / 1e9)
     dom = "estep_sweep2_kernel" if sw[..., 1].sum() >= sw[..., 0].sum() else "estep_sweep1_kernel"
     dom_gbs = min(s1_gbs, s2_gbs)
-    dsw = dense_arm["sweeps"].reshape(-1, 2)
+    dsw = dense_ev["sweeps"].reshape(-1, 2)
     d1, d2 = float(dsw[:, 0].mean()), float(dsw[:, 1].mean())
     alg_dense = 4.0 * NA * cols
     traffic = None
@@ -494,11 +501,14 @@ def main():
         "bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": dom_gbs / peak_gbs,
         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
         "traffic": traffic,
-        "definition": "sum over the timed launches of 4 B x cell pairs the launch must read (visited tiles) / sum of "
-                      "CUDA-event launch durations",
+        "definition": "sum over the launches of 4 B x cell pairs the launch must read (visited tiles) / sum of CUDA-event "
+                      "launch durations; the events are recorded in extra steps of the same workload right after the timed "
+                      "ones, kernel by kernel (the timed steps replay whole iterations from CUDA graphs, which leaves no "
+                      "room for events between kernels); ms_per_step_with_events shows the two agree",
+        "ms_per_step_with_events": main_ev["ms"],
         "sweep1_GBs": s1_gbs, "sweep2_GBs": s2_gbs,
         "visited_pair_fraction": float(vis.sum() / (tiles_all * vis.size)),
-        "sweeps_share_of_step": float(sw.sum() / sw.shape[0] / ms_per_step),
+        "sweeps_share_of_step": float(sw.sum() / sw.shape[0] / main_ev["ms"]),
         "dense": {
             "note": "same kernels with culling off: every launch reads all N_A x N_B pairs (4 B each)",
             "value": pairs_per_step * world / (dense_arm["ms"] * 1e-3), "ms_per_step": dense_arm["ms"],

@@ -143,7 +143,7 @@ typedef struct spb_em_params {
   double* Sigma;               /* [K][K] pinv(SigmaInv) */
   double* Coff;                /* [K][3] */
   double* moments;             /* [32] rigid-update moment accumulator */
-  double* jacobi_ws;           /* [2*K*K + 2*K] workspace of the eigen-solver */
+  double* jacobi_ws;           /* [1 + K*K] eigenbasis of the previous non-rigid solve ([0] = K once valid): Jacobi warm start, or NULL */
   const float* UT_hi;          /* [K][ldx] tf32 split of the row-centred UT (tensor-core K^T P K contraction), or NULL = SIMT path */
   const float* UT_lo;          /* [K][ldx] */
   const float* UT_mean;        /* [K] row means of UT (spb_gram_center) */
@@ -246,6 +246,10 @@ int spb_rigid_solve(const spb_em_params* p, int32_t iter, void* stream);     /* 
 int spb_row_update(const spb_em_params* p, void* stream);                    /* morpho_class.py:1404,293,1087 */
 /* full iteration = all of the above in reference order; needs K <= SPB_MAX_K_FUSED (else call the pieces) */
 int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream);    /* morpho_class.py:280-294 */
+/* same launch sequence with the non-rigid phase chosen by the caller; iter < 0: the iteration index is the device counter
+   spb_scalars.iter + 1 (SVI batch, step size, the iter < 100 sigma2 floor and the trace row all follow it), so ONE captured
+   CUDA graph of this call replays every iteration of a phase */
+int spb_em_iteration_ex(const spb_em_params* p, int32_t iter, int32_t nonrigid, void* stream);
 /* closing similarity from the last E-step's statistics: out = optimal_R[9], optimal_t[3] (device doubles) */
 int spb_optimal_rigid(const spb_em_params* p, double* out12, void* stream);  /* morpho_class.py:1451-1468 */
 

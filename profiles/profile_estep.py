@@ -17,13 +17,17 @@ ap.add_argument("--genes", type=int, default=2000)
 ap.add_argument("--iters", type=int, default=4)
 ap.add_argument("--start", type=int, default=0)
 ap.add_argument("--nn-init", type=int, default=0)
+ap.add_argument("--svi", type=int, default=0)
+ap.add_argument("--K", type=int, default=15)
+ap.add_argument("--graph", type=int, default=0, help="1: replay iterations from CUDA graphs (the product default)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 A, B = bench.make_pair_on_device(a.cells, a.genes, 3, 0, dev)
 np.random.seed(0)
-m = st.align.Morpho_pairwise(B, A, SVI_mode=False, max_iter=200, K=15, nn_init=bool(a.nn_init), verbose=False, device="0",
+m = st.align.Morpho_pairwise(B, A, SVI_mode=bool(a.svi), max_iter=200, K=a.K, nn_init=bool(a.nn_init), verbose=False, device="0",
                              materialize_P=False)
 m.prepare()
+m.use_cuda_graph = bool(a.graph)
 m.run_em(n_iter=a.iters, start=a.start)
 torch.cuda.synchronize()
 print("done", m._read_scalars().sigma2)

@@ -141,6 +141,7 @@ def load_library():
         "spb_rigid_solve": ([EP, I32, P], C.c_int),
         "spb_row_update": ([EP, P], C.c_int),
         "spb_em_iteration": ([EP, I32, P], C.c_int),
+        "spb_em_iteration_ex": ([EP, I32, I32, P], C.c_int),
         "spb_optimal_rigid": ([EP, P, P], C.c_int),
         "spb_rbf_kernel_T": ([P, I64, I64, P, I32, F, P, P], C.c_int),
         "spb_field_eval": ([P, I64, I32, P, P, I32, D, P, P], C.c_int),

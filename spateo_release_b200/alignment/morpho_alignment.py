@@ -39,6 +39,14 @@ def _validate_models(models, models_path):
     assert all(os.path.exists(os.path.join(models_path, m)) for m in models), "Some files in models_path do not exist."
 
 
+def _working_copy(model):
+    """The drivers never mutate their inputs (morpho_alignment.py:67): they work on copies. ``AnnDataLite`` copies share
+    the (read-only) expression matrices; a real ``AnnData`` is copied with its own ``.copy()``."""
+    from ..anndata_lite import AnnDataLite
+
+    return model.copy(share_X=True) if isinstance(model, AnnDataLite) else model.copy()
+
+
 def _seed_keys(slices, spatial_key, key_added):
     """Every slice starts with its raw coordinates under the three result keys (morpho_alignment.py:68-72)."""
     for sl in slices:
@@ -75,7 +83,7 @@ def morpho_align(
 ) -> Tuple[List, List[np.ndarray]]:
     """Serial alignment of consecutive slices; pair i+1 starts from pair i's aligned coordinates
     (morpho_alignment.py:22-111). Returns ``(align_models, pis)`` with ``pis[i] = P.T``."""
-    aligned = [m.copy() for m in models]
+    aligned = [_working_copy(m) for m in models]
     _seed_keys(aligned, spatial_key, key_added)
     pis = []
     for fixed, moving in zip(aligned[:-1], aligned[1:]):
@@ -213,8 +221,8 @@ def morpho_align_ref(
         for m in models:
             n = m.shape[0]
             models_ref.append(m[np.sort(np.random.choice(n, min(n_sampling, n), replace=False))].copy())
-    full = [m.copy() for m in models]
-    small = [m.copy() for m in models_ref]
+    full = [_working_copy(m) for m in models]
+    small = [_working_copy(m) for m in models_ref]
     _seed_keys(full + small, spatial_key, key_added)
     pis, pis_ref = [], []
     for i in range(len(full) - 1):

@@ -346,6 +346,7 @@ class Morpho_pairwise:
         self.materialize_P = materialize_P
         self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
+        self.use_cuda_graph = os.environ.get("SPB_CUDA_GRAPH", "1") != "0"
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64
         self._check()
@@ -556,8 +557,11 @@ class Morpho_pairwise:
         ib = np.random.choice(self.NB, n_sampling, replace=False) if self.NB > n_sampling else np.arange(self.NB)
         cA, cB = self.coordsA[ia, :], self.coordsB[ib, :]
         N, M, D = cA.shape[0], cB.shape[0], cA.shape[1]
-        XA = U.get_rep(self.sampleA[ia], self.init_layer, self.init_field, self.genes, self._np_dtype)
-        XB = U.get_rep(self.sampleB[ib], self.init_layer, self.init_field, self.genes, self._np_dtype)
+        XA = self._device_rows(self.init_layer, self.init_field, "A", ia)
+        XB = self._device_rows(self.init_layer, self.init_field, "B", ib)
+        if XA is None or XB is None:  # an initialisation layer that is not part of the alignment: host extraction
+            XA = U.get_rep(self.sampleA[ia], self.init_layer, self.init_field, self.genes, self._np_dtype)
+            XB = U.get_rep(self.sampleB[ib], self.init_layer, self.init_field, self.genes, self._np_dtype)
         import time as _time
 
         _t = _time.perf_counter()
@@ -644,8 +648,11 @@ class Morpho_pairwise:
         used = counts > 0
         new_id = (torch.cumsum(used.to(torch.int32), 0) - 1).to(torch.int32)
         n_used = int(used.sum().item())
-        ex = torch.from_numpy(np.ascontiguousarray(gene_exp, dtype=np.float32)).to(dev)
-        _count_h2d(ex)
+        if torch.is_tensor(gene_exp):
+            ex = gene_exp.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            ex = torch.from_numpy(np.ascontiguousarray(gene_exp, dtype=np.float32)).to(dev)
+            _count_h2d(ex)
         G = ex.shape[1]
         means = torch.zeros((n_used, G), dtype=torch.float64, device=dev)
         check(lib.spb_voxel_accumulate(*geom, ptr(counts), ptr(new_id), ptr(ex), G, G, ptr(means), G, stp),
@@ -700,7 +707,13 @@ class Morpho_pairwise:
                 continue
             sa = np.random.choice(self.NA, subsample, replace=False) if self.NA > subsample else np.arange(self.NA)
             sb = np.random.choice(self.NB, subsample, replace=False) if self.NB > subsample else np.arange(self.NB)
-            ET, nA = self._raw_cost_T(eA[sa], eB[sb], d_s)
+            if d_s == "label":
+                ET, nA = self._raw_cost_T(eA[sa], eB[sb], d_s)
+            else:  # gather the sub-samples on the device from the resident copies
+                dA, dB = self._to_device_pinned(eA), self._to_device_pinned(eB)
+                to_dev = lambda ix: torch.from_numpy(np.ascontiguousarray(ix, dtype=np.int64)).to(self._dev)
+                ET, nA = self._raw_cost_T(dA if sa.shape[0] == self.NA else dA.index_select(0, to_dev(sa)),
+                                          dB if sb.shape[0] == self.NB else dB.index_select(0, to_dev(sb)), d_s)
             mn = ET[:, :nA].min(dim=0).values  # min over fixed cells for every moving cell (utils: nx.min(exp_dist, 1))
             srt = torch.sort(mn).values
             val = float(srt[int(sa.shape[0] * 0.05)].item()) / 5
@@ -786,17 +799,36 @@ class Morpho_pairwise:
                 gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, G_eff, d_s, p_t, p_p, not first, self._GT, self.ldx)
                 del A, B, opA, opB
             first = False
+        self.__dict__.pop("_dev_rep", None)  # the resident copies of the representations are no longer needed
 
     def _to_device_pinned(self, host_array: np.ndarray) -> torch.Tensor:
-        """Host -> device copy of one dense representation: straight from pinned memory when ``pin_inputs`` staged it,
+        """Device copy of one dense representation, uploaded ONCE per preparation (the coarse initialisation, the beta^2
+        initialisation and the cost matrix all read it): straight from pinned memory when ``pin_inputs`` staged it,
         otherwise through the reusable pinned staging buffers."""
         key = id(host_array)
+        dcache = self.__dict__.setdefault("_dev_rep", {})
+        if key in dcache:
+            return dcache[key]
         cache = self.__dict__.setdefault("_pinned", {})
         self._h2d_bytes = getattr(self, "_h2d_bytes", 0) + host_array.size * 4
         if key in cache:
             _count_h2d(cache[key])
-            return cache[key].to(self._dev, non_blocking=True)
-        return staged_to_device(host_array, self._dev)
+            t = cache[key].to(self._dev, non_blocking=True)
+        else:
+            t = staged_to_device(host_array, self._dev)
+        dcache[key] = t
+        return t
+
+    def _device_rows(self, layer: str, field: str, side: str, idx: np.ndarray):
+        """Rows ``idx`` of a dense representation as a device tensor, gathered on the device when the representation is
+        one of the alignment's own layers (the usual case: init_layer == rep_layer); None when it is not."""
+        for r, f, eA, eB in zip(self.rep_layer, self.rep_field, self.exp_layers_A, self.exp_layers_B):
+            if r == layer and f == field and f != "obs":
+                full = self._to_device_pinned(eA if side == "A" else eB)
+                if idx.shape[0] == full.shape[0] and np.array_equal(idx, np.arange(full.shape[0])):
+                    return full
+                return full.index_select(0, torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(self._dev))
+        return None
 
     def pin_inputs(self):
         """Stage the dense representations in pinned host memory ahead of time (part of preprocessing)."""
@@ -890,11 +922,13 @@ class Morpho_pairwise:
         sc.sigma2 = float(self._sigma2_init)
         sc.sigma2_variance = 1.0
         sc.gamma = 0.5
+        sc.iter = -1  # device-side iteration counter: graph replays advance it (spb_em_iteration_ex)
         for q in range(9):
             sc.R[q] = 1.0 if q in (0, 4, 8) else 0.0
         host_sc = np.frombuffer(bytes(sc), dtype=np.uint8).copy()
         s["sc"] = torch.from_numpy(host_sc).to(dev)
         self._state = s
+        self.__dict__.pop("_graphs", None)  # captured iteration graphs hold the old state's pointers
         # params
         p = SpbEmParams()
         p.NA, p.NB, p.NBb, p.D, p.K, p.ldx = NA, NB, nbb, D, K, ldx
@@ -947,7 +981,9 @@ class Morpho_pairwise:
                      "trace_buf"):
             t = s[name]
             setattr(p, name, None if t is None else t.data_ptr())
-        p.jacobi_ws = None
+        # eigenbasis of the previous non-rigid solve (warm start of the in-library Jacobi); [0] = K once valid
+        s["jacobi_ws"] = torch.zeros((1 + K * K,), dtype=f64, device=dev) if K <= _capi.MAX_K_FUSED else None
+        p.jacobi_ws = None if s["jacobi_ws"] is None else s["jacobi_ws"].data_ptr()
         p.colmask = s["colmask"].data_ptr() if "colmask" in s else None
         # K^T P K contraction: tcgen05 (3xTF32) above 32 inducing points, exact fp64 SIMT kernel for small K
         backend = os.environ.get("SPB_GRAM", "auto")
@@ -1128,23 +1164,60 @@ class Morpho_pairwise:
     def run_em(self, n_iter: Optional[int] = None, start: int = 0, sweep_events: Optional[list] = None):
         """Enqueue EM iterations [start, start + n_iter) on the current stream (no host synchronisation).
 
+        Runs of iterations of the same phase (rigid-only up to ``nonrigid_start_iter``, with the non-rigid solve after) are
+        replayed from ONE captured CUDA graph of the iteration's launch sequence (``use_cuda_graph``, default on; the
+        iteration index — SVI batch, step size, trace row — is a device counter). Iterations that need host involvement
+        (history recording, per-sweep events, the posterior capture of the last iteration, K > SPB_MAX_K_FUSED in the
+        non-rigid phase) take the plain path.
+
         ``sweep_events``: optional list that receives (start, mid, end) CUDA events recorded around the two E-step sweep
         kernels of every iteration on the launching stream (bench.py's live roofline measurement)."""
         n_iter = self.max_iter - start if n_iter is None else n_iter
         with torch.cuda.device(self._dev):
             st = _capi.current_stream_ptr()
             hist = self._state.get("hist")
-            for it in range(start, start + n_iter):
+            it, end = start, start + n_iter
+            while it < end:
+                last = it == self.max_iter - 1
+                want_P = (self.materialize_P or self.compute_mapping) and last and not (self.return_mapping and self.SVI_mode)
+                nonrigid = it > self.nonrigid_start_iter
+                plain = (hist is not None or sweep_events is not None or want_P or _nvtx.enabled
+                         or not getattr(self, "use_cuda_graph", True) or (nonrigid and self.K > _capi.MAX_K_FUSED))
+                if not plain:
+                    # iterations [it, stop) share the phase and need nothing from the host
+                    stop = min(end, self.nonrigid_start_iter + 1) if not nonrigid else end
+                    if (self.materialize_P or self.compute_mapping) and stop == self.max_iter and not (self.return_mapping and self.SVI_mode):
+                        stop -= 1  # the last iteration captures the posterior: plain path
+                    if stop - it >= 3:
+                        self._iteration(it, st)  # explicit index: also the warm-up launch of every kernel of the phase
+                        graph, n_kernels = self._iteration_graph(nonrigid)
+                        for _ in range(it + 1, stop):
+                            graph.replay()
+                        # kernels launched through graph replays are not seen by the library's launch counter
+                        self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + n_kernels * (stop - it - 1)
+                        it = stop
+                        continue
                 if hist is not None:
                     hist[it].copy_(self._state["XAHat"])
                     self._state["hist_sigma2"][it].copy_(self._state["sc"][:8].view(torch.float64)[0])
-                last = it == self.max_iter - 1
                 if _nvtx.enabled:
                     torch.cuda.nvtx.range_push(f"em_iteration_{it}")
-                want_P = (self.materialize_P or self.compute_mapping) and last and not (self.return_mapping and self.SVI_mode)
                 self._iteration(it, st, capture_P=want_P, sweep_events=sweep_events)
                 if _nvtx.enabled:
                     torch.cuda.nvtx.range_pop()
+                it += 1
+
+    def _iteration_graph(self, nonrigid: bool):
+        """CUDA graph of one EM iteration of the given phase (captured once per device state)."""
+        graphs = self.__dict__.setdefault("_graphs", {})
+        if nonrigid not in graphs:
+            g = torch.cuda.CUDAGraph()
+            n0 = self._lib.spb_launch_count()
+            with torch.cuda.graph(g):
+                check(self._lib.spb_em_iteration_ex(C.byref(self._params), -1, 1 if nonrigid else 0, _capi.current_stream_ptr()),
+                      "spb_em_iteration_ex(capture)")
+            graphs[nonrigid] = (g, int(self._lib.spb_launch_count() - n0))
+        return graphs[nonrigid]
 
     @torch.no_grad()
     def run(self):

@@ -45,18 +45,21 @@ def check_spatial_coords(sample, spatial_key: str = "spatial") -> np.ndarray:
     coordinates = coordinates[:, keep]
     if coordinates.shape[1] > 3 or coordinates.shape[1] < 2:
         raise ValueError(f"The spatial coordinate '{spatial_key}' should only has 2 / 3 dimension")
-    return np.ascontiguousarray(coordinates)
+    return np.asarray(coordinates)  # column-major after the fancy column selection, like the reference's (see normalize_coords)
 
 
 def check_exp(sample, layer: str = "X") -> np.ndarray:
     """utils.py:112-135 — dense expression matrix of ``.X`` or ``.layers[layer]``."""
     if layer == "X":
-        m = sample.X.copy()
+        m = sample.X
     else:
         if layer not in sample.layers:
             raise KeyError(f"Layer '{layer}' not found in AnnData object.")
-        m = sample.layers[layer].copy()
-    return to_dense_matrix(m)
+        m = sample.layers[layer]
+    # The reference copies here (utils.py:127-131) because its backend later normalises in place; this package never
+    # writes into a representation (the device holds the working copies), so a dense input is passed through as a view
+    # and an 800 MB matrix is not duplicated twice per slice.
+    return m.toarray() if issparse(m) else np.asarray(m)
 
 
 def check_obs(rep_layer: List[str], rep_field: List[str]) -> Optional[str]:
@@ -158,19 +161,24 @@ def get_rep(sample, rep: str = "X", rep_field: str = "layer", genes=None, dtype=
 
 
 def normalize_coords(coordsA: np.ndarray, coordsB: np.ndarray, separate_mean=True, separate_scale=False):
-    """morpho_class.py:589-635 — zero-mean per slice, RMS scale (shared by default). Returns new arrays + params."""
+    """morpho_class.py:589-635 — zero-mean per slice, RMS scale (shared by default). Returns new arrays + params.
+
+    The arithmetic follows the reference operation by operation IN THE ARRAYS' OWN DTYPE AND MEMORY LAYOUT (einsum
+    reductions of the float32, column-major arrays ``check_spatial_coords`` returns): the coarse initialisation downstream
+    sits on a knife edge — ``np.arange(lo, hi, (hi - lo) / n)`` yields n or n + 1 voxel-grid points depending on the last
+    bit of ``lo`` / ``hi`` — so a one-ulp difference here changes the voxel set, the inlier pairs and the initial pose."""
     dt = coordsA.dtype
-    coords = [coordsA.copy(), coordsB.copy()]
+    coords = [coordsA.copy(order="K"), coordsB.copy(order="K")]
     D = coordsA.shape[1]
     means = np.zeros((2, D), dtype=dt)
     scales = np.zeros((2,), dtype=dt)
     for i in range(2):
-        means[i] = coords[i].sum(axis=0, dtype=np.float64) / coords[i].shape[0]
+        means[i] = np.einsum("ij->j", coords[i]) / coords[i].shape[0]
     if not separate_mean:
         means = np.repeat(means.mean(axis=0), 2, axis=0)  # same (odd) behaviour as morpho_class.py:615
     for i in range(2):
         coords[i] -= means[i]
-        scales[i] = np.sqrt(np.sum(coords[i].astype(np.float64) ** 2) / coords[i].shape[0])
+        scales[i] = np.sqrt(np.einsum("ij->", np.einsum("ij,ij->ij", coords[i], coords[i])) / coords[i].shape[0])
     if not separate_scale:
         scales = np.full((2,), scales.mean(), dtype=dt)
     for i in range(2):

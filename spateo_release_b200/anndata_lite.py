@@ -60,9 +60,18 @@ class AnnDataLite:
         return list(self.obsm.keys())
 
     # ---- copying / slicing --------------------------------------------------
-    def copy(self):
+    def copy(self, share_X: bool = False):
+        """Deep copy like ``AnnData.copy()``. ``share_X=True`` keeps ``.X`` / ``.layers`` by reference (the alignment
+        drivers only ever write ``.obsm`` / ``.uns`` of their working copies, so the expression matrices — 800 MB per
+        100k-cell slice — need not be duplicated)."""
         import copy as _copy
 
+        if share_X:
+            return AnnDataLite(
+                X=self.X, obs=self.obs.copy(), var=self.var.copy(),
+                obsm={k: (v.copy() if hasattr(v, "copy") else v) for k, v in self.obsm.items()},
+                layers=dict(self.layers), uns=_copy.deepcopy(self.uns),
+            )
         return AnnDataLite(
             X=self.X.copy(),
             obs=self.obs.copy(),

@@ -39,6 +39,12 @@ struct __align__(16) SmemLayoutT {
 struct ColRange {
   int begin, end;
 };
+// SVI: the column batch of the CURRENT iteration (morpho_class.py:894-896). The iteration index is read from the device
+// scalars (spb_iter_begin writes it), so a captured CUDA graph of one iteration can be replayed for every iteration.
+__device__ __forceinline__ const int32_t* batch_cols(const int32_t* __restrict__ batch_base, const spb_scalars* __restrict__ sc,
+                                                     int NBb) {
+  return batch_base ? batch_base + (int64_t)sc->iter * NBb : nullptr;
+}
 template <int kColStage>
 __device__ __forceinline__ ColRange col_range(const int32_t* __restrict__ colcount, int rb, int seg, int nseg) {
   const int count = colcount[rb];
@@ -282,7 +288,7 @@ __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const floa
 // ---------------------------------------------------------------------------------------------------------------------
 template <int kColStage, int kStages, int kMinBlocks>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colgeom, const float* __restrict__ XA, const float* __restrict__ lm,
                     const float* __restrict__ mm, const spb_scalars* __restrict__ sc, float* __restrict__ colpart,
                     int NBb, int nbb_pad, const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
@@ -294,6 +300,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const int i0 = rb * kRowTile;
   const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
   const int32_t* list = collist + (int64_t)rb * nbb_pad;
+  const int32_t* col_index = batch_cols(batch_base, sc, NBb);
   if (cr.begin >= cr.end) return;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -372,7 +379,7 @@ __global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, 
 // ---------------------------------------------------------------------------------------------------------------------
 template <int kColStage, int kStages, int kMinBlocks, bool kSparse, int kDbg = 0>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                     const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int nbb_pad,
                     const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
@@ -384,6 +391,7 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const int i0 = rb * kRowTile;
   ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
   const int32_t* list = collist + (int64_t)rb * nbb_pad;
+  const int32_t* col_index = batch_cols(batch_base, sc, NBb);
   const int j_begin = cr.begin, j_end = cr.end;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -483,12 +491,17 @@ __global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restri
 // A column j is dropped when c_q * dmin^2 < -127 (log2 domain, with a 1e-5 relative safety margin), dmin = distance from
 // y_j to the block's bounding box: then ex2(c_q d + lm) and ex2(c_s d) flush to +0 for every pair of the block (lm <= 0,
 // c_s <= c_q < 0), so the dropped pairs would have added exact zeros.
-__global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
-                                                               int NBb, spb_scalars* __restrict__ sc, int cull,
-                                                               int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
-                                                               int nbb_pad, uint32_t* __restrict__ colmask) {
+// One CTA per row block, 32 warps, each warp owns a contiguous range of columns: pass 1 evaluates the test once (the keep
+// bits go to shared memory), one block barrier turns the per-warp counts into offsets, pass 2 scatters. The partial column
+// sums of the DROPPED (row block, column) combinations are zeroed here, so sweep 1 needs no 157 MB memset per iteration.
+constexpr int kListThreads = 1024;
+__global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
+                                                                       int NBb, spb_scalars* __restrict__ sc, int cull,
+                                                                       int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
+                                                                       int nbb_pad, uint32_t* __restrict__ colmask,
+                                                                       float* __restrict__ colpart) {
+  extern __shared__ uint32_t keep_bits[];  // one word per 32 columns
   __shared__ int warp_cnt[32];
-  __shared__ int base;
   const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float cq = sc->c_q * (1.0f - 1e-5f);
   float lo[3], hi[3];
@@ -497,71 +510,70 @@ __global__ void __launch_bounds__(1024) build_col_lists_kernel(const float* __re
     lo[d] = bbox[rb * 8 + d];
     hi[d] = bbox[rb * 8 + 3 + d];
   }
-  if (threadIdx.x == 0) base = 0;
-  __syncthreads();
-  int32_t* list = collist + (int64_t)rb * nbb_pad;
-  constexpr int kPer = 4;  // columns per thread per round: 4096 columns between block-wide barriers
-  for (int j0 = 0; j0 < NBb; j0 += 1024 * kPer) {
-    const int jt = j0 + threadIdx.x * kPer;
-    unsigned bits = 0u;
+  const int nwords = (NBb + 31) / 32;
+  const int wpw = (nwords + 31) / 32;  // words per warp
+  const int w0 = warp * wpw, w1 = min(nwords, w0 + wpw);
+  int cnt = 0;
+  for (int wd = w0; wd < w1; ++wd) {
+    const int j = wd * 32 + lane;
+    bool keep = false;
+    if (j < NBb) {
+      keep = true;
+      if (cull) {
+        const float* y = colgeom + (int64_t)j * 8;
+        float d2 = 0.f;
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      const int j = jt + q;
-      bool keep = false;
-      if (j < NBb) {
-        keep = true;
-        if (cull) {
-          const float* y = colgeom + (int64_t)j * 8;
-          float d2 = 0.f;
-#pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const float yd = y[2 * d];
-            const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
-            d2 = fmaf(g, g, d2);
-          }
-          keep = cq * d2 >= -127.0f;
+        for (int d = 0; d < 3; ++d) {
+          const float yd = y[2 * d];
+          const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
+          d2 = fmaf(g, g, d2);
         }
+        keep = cq * d2 >= -127.0f;
       }
-      bits |= (keep ? 1u : 0u) << q;
     }
-    const int c = __popc(bits);
-    int inc = c;  // inclusive scan of the per-thread counts inside the warp
+    const uint32_t bits = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) keep_bits[wd] = bits;
+    cnt += __popc(bits);
+  }
+  if (lane == 0) warp_cnt[warp] = cnt;
+  __syncthreads();
+  int off = 0, total = 0;
+  {
+    const int c = warp_cnt[lane];
+    int inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
-    if (lane == 31) warp_cnt[warp] = inc;
-    __syncthreads();
-    int off = base + inc - c;
-    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    off = __shfl_sync(0xffffffffu, inc - c, warp);   // exclusive prefix of this warp
+    total = __shfl_sync(0xffffffffu, inc, 31);
+  }
+  int32_t* list = collist + (int64_t)rb * nbb_pad;
+  for (int wd = w0; wd < w1; ++wd) {
+    const uint32_t bits = keep_bits[wd];
+    const int j = wd * 32 + lane;
+    if ((bits >> lane) & 1u) {
+      list[off + __popc(bits & ((1u << lane) - 1u))] = j;
+      if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
+    } else if (j < NBb) {
 #pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-      if ((bits >> q) & 1u) {
-        const int j = jt + q;
-        list[off++] = j;
-        if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
-      }
+      for (int v = 0; v < 4; ++v) colpart[((int64_t)rb * 4 + v) * nbb_pad + j] = 0.f;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int w = 0; w < 32; ++w) t += warp_cnt[w];
-      base += t;
-    }
-    __syncthreads();
+    off += __popc(bits);
   }
   if (threadIdx.x == 0) {
-    colcount[rb] = base;
-    atomicAdd(&sc->visited, (double)base);
+    colcount[rb] = total;
+    atomicAdd(&sc->visited, (double)total);
   }
 }
 
 // gather this iteration's fixed-slice coordinates (SVI batch or all columns) (morpho_class.py:1149)
-__global__ void gather_cols_kernel(const float* __restrict__ xb4, const int32_t* __restrict__ idx, int NBb,
-                                   float* __restrict__ colgeom) {
+__global__ void gather_cols_kernel(const float* __restrict__ xb4, const int32_t* __restrict__ batch_base,
+                                   const spb_scalars* __restrict__ sc, int NBb, float* __restrict__ colgeom) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= NBb) return;
+  const int32_t* idx = batch_cols(batch_base, sc, NBb);
   const int64_t src = idx ? idx[j] : j;
   const float4 y = reinterpret_cast<const float4*>(xb4)[src];
   float4* out = reinterpret_cast<float4*>(colgeom + (int64_t)j * 8);
@@ -570,11 +582,12 @@ __global__ void gather_cols_kernel(const float* __restrict__ xb4, const int32_t*
 }
 
 // dense P for the caller (utils.py:1083): P[i][j] = qm_ij g_ij c_j, transposed through shared memory
-__global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+__global__ void materialize_P_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                                      const float* __restrict__ colconst, const float* __restrict__ XA,
                                      const float* __restrict__ lm, const spb_scalars* __restrict__ sc, int NA, int NBb,
                                      float* __restrict__ P, int64_t ldp) {
   __shared__ float tile[32][33];
+  const int32_t* col_index = batch_cols(batch_base, sc, NBb);
   const float c_q = sc->c_q;
   const int jb = blockIdx.y * 32, ib = blockIdx.x * 32;
   for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
@@ -666,7 +679,7 @@ __device__ __forceinline__ float sel_block_sum(float v, float* red) {
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                   float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                   const spb_scalars* __restrict__ sc, int NA, int topk, float* __restrict__ K_NB,
                   const uint32_t* __restrict__ colmask) {
@@ -679,6 +692,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   const int jb = blockIdx.x;
   float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
   const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
+  const int32_t* col_index = batch_cols(batch_base, sc, (int)gridDim.x);
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   const float* g = GT + row * ldx;
   const float cq = sc->c_q;
@@ -819,7 +833,7 @@ col_select_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
 // with fewer than k non-zero weights (the reference's sort keeps exactly k entries per column). Unordered within the
 // column; the host sorts the k values.
 __global__ void __launch_bounds__(kSelThreads)
-col_emit_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+col_emit_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                 const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                 const spb_scalars* __restrict__ sc, int NA, int topk, int32_t* __restrict__ rows,
                 float* __restrict__ vals) {
@@ -827,6 +841,7 @@ col_emit_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __rest
   const int jb = blockIdx.x, tid = threadIdx.x;
   const float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
   const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10], tau = cc[18];
+  const int32_t* col_index = batch_cols(batch_base, sc, (int)gridDim.x);
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   const float* g = GT + row * ldx;
   const float cq = sc->c_q;
@@ -883,13 +898,14 @@ __device__ __forceinline__ unsigned long long argmax_key(float p, int idx) {
 }
 
 __global__ void __launch_bounds__(kSelThreads)
-col_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+col_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                   const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                   const spb_scalars* __restrict__ sc, int NA, unsigned long long* __restrict__ colbest) {
   __shared__ unsigned long long red[kSelThreads / 32];
   const int jb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* cc = colconst + (int64_t)jb * SPB_COLCONST_FLOATS;
   const float y0 = cc[0], y1 = cc[2], y2 = cc[4], cj = cc[10];
+  const int32_t* col_index = batch_cols(batch_base, sc, (int)gridDim.x);
   const int64_t row = col_index ? (int64_t)col_index[jb] : (int64_t)jb;
   unsigned long long best = 0ull;
   sel_for_each(GT + row * ldx, XA, ldx, lm, NA, y0, y1, y2, sc->c_q, [&](int i, float w) {
@@ -911,7 +927,7 @@ col_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
 
 // one thread per moving cell, blockIdx.y = column segment; partial results are merged with a 64-bit atomicMax
 __global__ void __launch_bounds__(256)
-row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ col_index,
+row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                   const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                   const spb_scalars* __restrict__ sc, int NA, int NBb, unsigned long long* __restrict__ rowbest) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -919,6 +935,7 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
   const int per = (NBb + gridDim.y - 1) / gridDim.y;
   const int j0 = blockIdx.y * per, j1 = min(NBb, j0 + per);
   const float x0 = XA[i], x1 = XA[ldx + i], x2 = XA[2 * ldx + i], li = lm[i], cq = sc->c_q;
+  const int32_t* col_index = batch_cols(batch_base, sc, NBb);
   unsigned long long best = 0ull;
   for (int j = j0; j < j1; ++j) {
     const float4 c0 = *reinterpret_cast<const float4*>(colconst + (int64_t)j * SPB_COLCONST_FLOATS);
@@ -970,12 +987,13 @@ int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
 
 }  // namespace
 
-static inline const int32_t* batch_ptr(const spb_em_params* p, int iter) {
-  return (p->svi && p->batch_idx) ? p->batch_idx + (int64_t)iter * p->NBb : nullptr;
+// base of the SVI batch schedule [max_iter][NBb]; the kernels pick the row of the current iteration (sc->iter)
+static inline const int32_t* batch_ptr(const spb_em_params* p, int /*iter*/) {
+  return (p->svi && p->batch_idx) ? p->batch_idx : nullptr;
 }
 
 extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* stream) {
-  gather_cols_kernel<<<(p->NBb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p->xb4, batch_ptr(p, iter), p->NBb, p->colgeom);
+  gather_cols_kernel<<<(p->NBb + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p->xb4, batch_ptr(p, iter), p->sc, p->NBb, p->colgeom);
   SPB_CHECK_LAUNCH();
   return 0;
 }
@@ -998,18 +1016,25 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
     cudaError_t e = cudaMemsetAsync(colmask, 0, sizeof(uint32_t) * SPB_COLMASK_WORDS * (size_t)p->nbb_pad, (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
-  build_col_lists_kernel<<<nrb, 1024, 0, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
-                                                                 p->colcount, p->nbb_pad, colmask);
+  const size_t smem = sizeof(uint32_t) * (size_t)((p->NBb + 31) / 32);
+  if (smem > 200 * 1024) return SPB_EUNSUPPORTED;  // 1.6 M columns per iteration
+  static bool attr_set[SPB_MAX_DEVICES] = {};
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(build_col_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev_] = true;
+  }
+  build_col_lists_kernel<<<nrb, kListThreads, smem, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
+                                                                            p->colcount, p->nbb_pad, colmask, p->colpart);
   SPB_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
-  {  // partial column sums of (row block, column) combinations that are not visited must read as zero
-    cudaError_t e = cudaMemsetAsync(p->colpart, 0, sizeof(float) * (size_t)(p->ldx / kRowTile) * 4 * p->nbb_pad, (cudaStream_t)stream);
-    if (e != cudaSuccess) return (int)e;
-  }
+  // partial column sums of (row block, column) combinations that are not visited read as zero: spb_estep_col_lists zeroes
+  // exactly those entries, every other entry is overwritten by this launch
   if (g_sweep_cfg == 1) rc = launch_sweep1<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep1<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep1<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);

@@ -216,14 +216,16 @@ __global__ void gram_reduce_kernel(const GramPlan plan, const float* __restrict_
     return;
   }
   const bool ha = gram_entry(plan, scratch, k, l, a), hb = gram_entry(plan, scratch, l, k, b);
-  const double g = (ha && hb) ? 0.5 * (a + b) : (ha ? a : b);
+  const double g = (ha && hb) ? 0.5 * (k <= l ? __dadd_rn(a, b) : __dadd_rn(b, a)) : (ha ? a : b);
   double vk = 0.0, vl = 0.0;  // v = D^T w
   gram_entry(plan, scratch, k, K + E, vk);
   gram_entry(plan, scratch, l, K + E, vl);
   const double ml = (double)mean[l];
   // the two cross terms are added in an order that does not depend on which of (k, l), (l, k) this thread owns
-  const double c1 = ml * vk, c2 = mk * vl;
-  UtWU[(int64_t)k * K + l] = g + (k <= l ? c1 + c2 : c2 + c1) + mk * ml * sums[0];
+  // (explicit rounding of every operation: an fma contraction chosen differently on the two sides would break symmetry)
+  const double c1 = __dmul_rn(ml, vk), c2 = __dmul_rn(mk, vl);
+  const double cross = k <= l ? __dadd_rn(c1, c2) : __dadd_rn(c2, c1);
+  UtWU[(int64_t)k * K + l] = __dadd_rn(__dadd_rn(g, cross), __dmul_rn(__dmul_rn(mk, ml), sums[0]));
 }
 
 // Row means of U^T and the centred, tf32-split A operand (once per alignment; U is constant over the EM).

@@ -13,6 +13,7 @@ constexpr double kTwoPi = 6.283185307179586;
 __global__ void iter_begin_kernel(spb_em_params p, int iter) {
   spb_scalars* sc = p.sc;
   const int K = p.K;
+  if (iter < 0) iter = sc->iter + 1;  // graph replay: the iteration counter lives on the device
   for (int q = threadIdx.x; q < K * K; q += blockDim.x) p.UtWU[q] = 0.0;
   for (int q = threadIdx.x; q < K * 3; q += blockDim.x) p.UtPXB[q] = 0.0;
   for (int q = threadIdx.x; q < 32; q += blockDim.x) p.moments[q] = 0.0;
@@ -308,6 +309,37 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
     }
   }
   __syncthreads();
+  // Warm start: SigmaInv changes little from one EM iteration to the next, so in the eigenbasis V0 of the previous
+  // iteration it is already nearly diagonal. Rotate A <- V0^T A V0 (two K^3 products in shared memory) and continue the
+  // Jacobi sweeps from V = V0: 2-4 sweeps instead of 8-10 from the identity.
+  double* ws = p.jacobi_ws;
+  const bool warm = ws != nullptr && ws[0] == (double)K;
+  if (warm) {
+    double* T = cs + Kp + Kp;  // [Kp][Kp] scratch behind the index arrays
+    const double* V0 = ws + 1;
+    for (int q = tid; q < Kp * Kp; q += nt) {
+      const int r = q / Kp, c = q % Kp;
+      V[q] = (r < K && c < K) ? V0[r * K + c] : (r == c ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    for (int q = tid; q < Kp * Kp; q += nt) {  // T = A V
+      const int r = q / Kp, c = q % Kp;
+      double t = 0.0;
+      for (int e = 0; e < Kp; ++e) t += A[r * Kp + e] * V[e * Kp + c];
+      T[q] = t;
+    }
+    __syncthreads();
+    for (int q = tid; q < Kp * Kp; q += nt) {  // A = V^T T (upper triangle, mirrored: exactly symmetric)
+      const int r = q / Kp, c = q % Kp;
+      if (r <= c) {
+        double t = 0.0;
+        for (int e = 0; e < Kp; ++e) t += V[e * Kp + r] * T[e * Kp + c];
+        A[r * Kp + c] = t;
+        A[c * Kp + r] = t;
+      }
+    }
+    __syncthreads();
+  }
   const int npair = Kp / 2;
   for (int sweep = 0; sweep < 30; ++sweep) {
     // convergence: off-diagonal mass below 1e-30 of the diagonal mass (eigenvalues then carry ~1e-15 relative error)
@@ -407,7 +439,9 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
     double s = 0;
     for (int e = 0; e < Kp; ++e) s += V[r * Kp + e] * cs[e] * V[c * Kp + e];
     p.Sigma[q] = s;
+    if (ws != nullptr) ws[1 + q] = V[r * Kp + c];  // eigenbasis for the next iteration's warm start
   }
+  if (ws != nullptr && tid == 0) ws[0] = (double)K;
   if (p.g_on && p.g_nonrigid) {  // U^T PXB_term += c_g U_I^T (X_BI - R_AI)   (:1286-1288)
     const double cg = sc->sigma2 * p.g_weight * sc->Sp / (double)p.g_NI;
     for (int q = tid; q < K * 3; q += nt) {
@@ -495,6 +529,7 @@ __global__ void __launch_bounds__(256) rigid_moments_kernel(spb_em_params p) {
 __global__ void rigid_solve_kernel(spb_em_params p, int iter) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   spb_scalars* sc = p.sc;
+  if (iter < 0) iter = sc->iter;
   const int D = p.D;
   const double* m = p.moments;
   const double Sp = sc->Sp, SpK = m[28];
@@ -771,15 +806,17 @@ extern "C" int spb_nonrigid_blend(const spb_em_params* p, void* stream) {
 extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
   if (p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
   const int Kp = (p->K + 1) & ~1;
-  const size_t smem = sizeof(double) * (2 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;
+  const size_t smem = sizeof(double) * (3 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;  // A, V, warm-start scratch, rotations, pairing
   static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(nonrigid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(nonrigid_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
-  nonrigid_solve_kernel<<<1, 256, smem, ST>>>(*p);
+  // small matrices are latency-bound on the block barriers of the rotation rounds: fewer threads, cheaper barriers
+  const int threads = Kp <= 16 ? 32 : (Kp <= 32 ? 64 : 256);
+  nonrigid_solve_kernel<<<1, threads, smem, ST>>>(*p);
   SPB_CHECK_LAUNCH();
   return 0;
 }
@@ -822,8 +859,10 @@ extern "C" int spb_optimal_rigid(const spb_em_params* p, double* out12, void* st
     if (rc__ != 0) return rc__; \
   } while (0)
 
-extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream) {
-  const bool nonrigid = iter > p->nonrigid_start_iter;  // latched flag == monotone in iter (morpho_class.py:289-291)
+// One EM iteration (morpho_class.py:280-294) as a fixed launch sequence. ``iter`` < 0: the iteration index is taken from
+// the device scalars (previous + 1), which makes the sequence capturable ONCE in a CUDA graph and replayable for every
+// iteration of a phase (``nonrigid`` = 0 before nonrigid_start_iter, 1 after).
+extern "C" int spb_em_iteration_ex(const spb_em_params* p, int32_t iter, int32_t nonrigid, void* stream) {
   if (nonrigid && p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
   SPB_TRY(spb_iter_begin(p, iter, stream));
   SPB_TRY(spb_gather_cols(p, iter, stream));
@@ -843,4 +882,10 @@ extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stre
   SPB_TRY(spb_rigid_solve(p, iter, stream));
   SPB_TRY(spb_row_update(p, stream));
   return 0;
+}
+
+extern "C" int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream) {
+  if (iter < 0) return SPB_EINVAL;
+  // latched flag == monotone in iter (morpho_class.py:289-291)
+  return spb_em_iteration_ex(p, iter, iter > p->nonrigid_start_iter ? 1 : 0, stream);
 }

@@ -93,6 +93,7 @@ def test_weighted_gram_fp64_kernels(K, N):
     check(lib.spb_weighted_gram(ptr(UT), ldn, N, K, ptr(wd), ptr(X3), ptr(G), ptr(R), _capi.current_stream_ptr()), "gram")
     torch.cuda.synchronize()
     U64, X64 = U.astype(np.float64), X.astype(np.float64)
-    wu = (U * w[:, None]).astype(np.float64)  # the kernels round w * u to fp32 like the reference's fp32 product
-    assert np.abs(G.cpu().numpy() - U64.T @ wu).max() < 1e-11 * np.abs(U64.T @ wu).max()
+    # the kernels round w * u to fp32 (like the reference's fp32 product) and mirror off-diagonal tiles: 1e-7 relative
+    want = U64.T @ (U64 * w.astype(np.float64)[:, None])
+    assert np.abs(G.cpu().numpy() - want).max() < 2e-7 * np.abs(want).max()
     assert np.abs(R.cpu().numpy() - U64.T @ X64).max() < 1e-11 * (np.abs(U64).T @ np.abs(X64)).max()

@@ -73,6 +73,22 @@ def test_normalize_coords_matches_oracle():
     assert a[0, 0] != ca[0, 0]  # inputs are not mutated
 
 
+@pytest.mark.parametrize("case", ["2d_full", "3d_svi", "3d_full_warp", "c1_2d_svi", "c1_2d_full_warp"])
+def test_normalisation_is_bitwise_the_references(golden, case):
+    """check_spatial_coords + normalize_coords of the PRODUCT reproduce the reference's float32 arrays to the last bit
+    (the coarse initialisation's np.arange voxel grid flips between n and n + 1 points on a one-ulp change)."""
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    g = golden(case)
+    A = AnnDataLite(np.zeros((g["raw_coords_moving"].shape[0], 1), np.float32), obsm={"spatial": g["raw_coords_moving"]})
+    B = AnnDataLite(np.zeros((g["raw_coords_fixed"].shape[0], 1), np.float32), obsm={"spatial": g["raw_coords_fixed"]})
+    ca = U.check_spatial_coords(A).astype(np.float32)
+    cb = U.check_spatial_coords(B).astype(np.float32)
+    _, nb, sc, mu = U.normalize_coords(ca, cb)
+    assert np.array_equal(nb, g["pre_coordsB"])
+    assert np.array_equal(sc, g["pre_normalize_scales"]) and np.array_equal(mu, g["pre_normalize_means"])
+
+
 def test_check_spatial_coords_errors():
     A, _ = make_slice_pair(50, 50, 5, dim=2)
     with pytest.raises(KeyError):
