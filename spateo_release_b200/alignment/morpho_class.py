@@ -423,10 +423,16 @@ class Morpho_pairwise:
             self.pre_compute_dist = False  # morpho_class.py:439-440 (no effect here: the cost matrix is always resident)
             if int(self.sparse_top_k) < 1:
                 raise ValueError("sparse_top_k must be a positive integer.")
-        if self.kernel_type != "euc":
-            if self.kernel_type == "geodist":
-                raise NotImplementedError("kernel_type='geodist' is not implemented in spateo_release_b200 yet.")
+        if self.kernel_type not in ("euc", "geodist"):
             raise NotImplementedError(f"Kernel type '{self.kernel_type}' is not implemented.")
+        if self.dtype != "float32":
+            # the reference honours dtype="float64" end to end (morpho_class.py:165, utils.py:35-66); the device kernels of
+            # this package compute in float32 (with fp64 reductions), so a float64 request is refused rather than served
+            # with narrower arithmetic
+            raise NotImplementedError(
+                f"dtype={self.dtype!r} is not implemented in spateo_release_b200: the device path computes in float32 "
+                "(fp64 reductions / solves); use dtype='float32'."
+            )
 
     # ------------------------------------------------------------------------------------------------------------------
     # preprocessing (morpho_class.py:443-558)
@@ -507,6 +513,9 @@ class Morpho_pairwise:
         # U^T on the device from the pre-initialisation coordinates (the reference builds U before the coarse init)
         self.ldx = _round_up(self.NA, _capi.ROW_TILE)
         dev = self._dev
+        if self.kernel_type == "geodist":
+            self._construct_geodesic_kernel()
+            return
         x_soa = torch.zeros((3, self.ldx), dtype=torch.float32, device=dev)
         x_soa[: self.D, : self.NA] = torch.from_numpy(np.ascontiguousarray(self.coordsA.T, dtype=np.float32)).to(dev)
         zt = torch.zeros((self.K, 3), dtype=torch.float32, device=dev)
@@ -517,6 +526,34 @@ class Morpho_pairwise:
                                        ptr(self._UT), _capi.current_stream_ptr()),
             "spb_rbf_kernel_T",
         )
+
+    def _construct_geodesic_kernel(self):
+        """``kernel_type="geodist"`` (morpho_class.py:865-871, utils.py:1161-1217): U = exp(-beta d_g^2) with d_g the
+        shortest-path distance on the k-nearest-neighbour graph of the moving cells, from every cell to the K inducing
+        cells; unreachable pairs get d_g = 1e5 like the reference. One-off host work (scipy's Dijkstra on the sparse graph
+        instead of the reference's dense N x N adjacency + networkx loop), the kernel matrix then lives on the device."""
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import dijkstra
+
+        N = self.NA
+        if self.graph is None:
+            from sklearn.neighbors import kneighbors_graph
+
+            adj = kneighbors_graph(self.coordsA, self.graph_knn, mode="distance", include_self=False)
+        elif sp.issparse(self.graph):
+            adj = sp.csr_matrix(self.graph)
+        else:  # a networkx graph, as the reference accepts
+            import networkx
+
+            adj = networkx.to_scipy_sparse_array(self.graph, nodelist=list(range(N)), weight="weight", format="csr")
+        adj = sp.csr_matrix(adj.maximum(adj.T))  # networkx.Graph is undirected: an edge exists if either end lists it
+        dist = dijkstra(adj, directed=False, indices=np.asarray(self.inducing_variables_idx, dtype=np.int64))  # [K, N]
+        dist = np.where(np.isfinite(dist), dist, 1e5)
+        UT64 = np.exp(-float(self.kernel_bandwidth) * dist**2)  # [K, N] float64 like the reference's
+        self.GammaSparse = np.ascontiguousarray(UT64[:, self.inducing_variables_idx].T, dtype=np.float32)
+        self.U_I = None  # guidance points are not nodes of the graph (morpho_class.py:871)
+        self._UT = torch.zeros((self.K, self.ldx), dtype=torch.float32, device=self._dev)
+        self._UT[:, :N] = torch.from_numpy(np.ascontiguousarray(UT64, dtype=np.float32)).to(self._dev)
 
     @property
     def U(self) -> np.ndarray:

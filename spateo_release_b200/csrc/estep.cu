@@ -346,15 +346,31 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
 // ---------------------------------------------------------------------------------------------------------------------
 // column constants
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void col_finalize_kernel(const float* __restrict__ colpart, int nrb, int nbb_pad, int NBb,
-                                    const float* __restrict__ colgeom, const spb_scalars* __restrict__ sc,
-                                    float* __restrict__ colconst, float* __restrict__ K_NB) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= NBb) return;
+// One warp owns 32 consecutive columns; the kFinWarps warps of a CTA split the row blocks between them (the fold over ~100
+// row-block partials per column is a chain of dependent loads otherwise) and combine through shared memory in fp64.
+constexpr int kFinWarps = 8;
+__global__ void __launch_bounds__(32 * kFinWarps)
+col_finalize_kernel(const float* __restrict__ colpart, int nrb, int nbb_pad, int NBb, const float* __restrict__ colgeom,
+                    const spb_scalars* __restrict__ sc, float* __restrict__ colconst, float* __restrict__ K_NB) {
+  __shared__ double part[kFinWarps][4][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
   double C[4] = {0, 0, 0, 0};
-  for (int rb = 0; rb < nrb; ++rb) {
+  if (j < NBb) {
+    for (int rb = warp; rb < nrb; rb += kFinWarps) {
 #pragma unroll
-    for (int v = 0; v < 4; ++v) C[v] += (double)colpart[((int64_t)rb * 4 + v) * nbb_pad + j];
+      for (int v = 0; v < 4; ++v) C[v] += (double)colpart[((int64_t)rb * 4 + v) * nbb_pad + j];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 4; ++v) part[warp][v][lane] = C[v];
+  __syncthreads();
+  if (warp != 0 || j >= NBb) return;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    double t = 0.0;
+    for (int w = 0; w < kFinWarps; ++w) t += part[w][v][lane];  // fixed order: deterministic
+    C[v] = t;
   }
   const double omega = sc->omega;
   const double inl = 1.0 - omega / (omega + C[0]);          // utils.py:1055
@@ -1044,7 +1060,7 @@ extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stre
 }
 
 extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
-  col_finalize_kernel<<<(p->NBb + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+  col_finalize_kernel<<<(p->NBb + 31) / 32, 32 * kFinWarps, 0, (cudaStream_t)stream>>>(
       p->colpart, p->ldx / kRowTile, p->nbb_pad, p->NBb, p->colgeom, p->sc, p->colconst, p->K_NB);
   SPB_CHECK_LAUNCH();
   return 0;

@@ -70,8 +70,16 @@ def SparseVFC(
     verbose: int = 1,
     ctrl_idx: Optional[np.ndarray] = None,
     device=None,
+    gram: str = "auto",
+    timings: Optional[dict] = None,
 ) -> dict:
-    """Sparse vector-field consensus (same signature as dynamo's ``SparseVFC``; ``ctrl_idx`` / ``device`` are extras).
+    """Sparse vector-field consensus (same signature as dynamo's ``SparseVFC``; ``ctrl_idx`` / ``device`` / ``gram`` /
+    ``timings`` are extras).
+
+    ``gram``: how the normal-equation blocks U^T P U and U^T P Y are contracted — ``"tensor"`` = tcgen05 kernel (3xTF32 on the
+    row-centred kernel matrix, fp64 fold; products carry fp32-level relative noise ~1e-7), ``"fp64"`` = SIMT kernels with
+    fp64 products, ``"auto"`` = tensor above 32 control points. ``timings``: dict that receives CUDA-event timings of the
+    EM loop (bench.py).
 
     Returns the dictionary documented at sparsevfc.py:139-157: X, valid_ind, X_ctrl, ctrl_idx, Y, beta, V, C, P, VFCIndex,
     sigma2, grid, grid_V, iteration, tecr_traj, E_traj.
@@ -120,6 +128,21 @@ def SparseVFC(
         A_d = torch.empty((M, M), dtype=torch.float64, device=dev)
         B_d = torch.empty((M, 3), dtype=torch.float64, device=dev)
         Cd = torch.zeros((M, 3), dtype=torch.float64, device=dev)
+        use_tc = gram == "tensor" or (gram == "auto" and M > 32)
+        if gram not in ("auto", "tensor", "fp64"):
+            raise ValueError("gram must be 'auto', 'tensor' or 'fp64'")
+        if use_tc:
+            import ctypes as C_
+
+            A_hi, A_lo = torch.empty_like(UT), torch.empty_like(UT)
+            u_mean = torch.empty((M,), dtype=torch.float32, device=dev)
+            check(lib.spb_gram_center(ptr(UT), ldn, N, M, ptr(u_mean), ptr(A_hi), ptr(A_lo), st), "spb_gram_center")
+            B_hi = torch.zeros((M + 4, ldn), dtype=torch.float32, device=dev)
+            B_lo = torch.zeros((M + 4, ldn), dtype=torch.float32, device=dev)
+            need = C_.c_int64(0)
+            check(lib.spb_gram_tc_scratch_floats(M, 3, N, C_.byref(need)), "spb_gram_tc_scratch_floats")
+            g_scratch = torch.empty((need.value,), dtype=torch.float32, device=dev)
+            g_sums = torch.zeros((4,), dtype=torch.float64, device=dev)
 
         Kd = torch.from_numpy(Kc).to(dev)
         sigma2 = max(float((Yv**2).sum() / (N * D)), 1e-7)
@@ -128,24 +151,52 @@ def SparseVFC(
         Y2 = (Yd**2).sum(1)  # |Y_i|^2, reused for sum P |Y|^2
         reg_energy = 0.0     # tr(C^T K C) of the current coefficients
         rcond = np.finfo(np.float64).eps * M
+        ev_pairs = [] if timings is not None else None
+        n_fallback = 0
         while it < MaxIter and tecr > ecr and sigma2 > 1e-8:
             E_old = E
+            if ev_pairs is not None:
+                evs = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                evs[0].record()
             check(
                 lib.spb_vfc_estep(ptr(UT), ldn, N, M, D, ptr(Cd), ptr(Yd), sigma2, gamma, float(a), float(minP),
                                   float(theta), ptr(P), ptr(V), ptr(Pf), ptr(PY3), ptr(sums), st),
                 "spb_vfc_estep",
             )
-            check(lib.spb_weighted_gram(ptr(UT), ldn, N, M, ptr(Pf), ptr(PY3), ptr(A_d), ptr(B_d), st), "spb_weighted_gram")
-            # M-step on the device: minimum-norm solution of (lambda sigma2 K + U^T P U) C = U^T P Y through the symmetric
-            # eigen-decomposition with lstsq's singular-value cutoff (the reference calls scipy.linalg.lstsq, sparsevfc.py:189)
+            if ev_pairs is not None:
+                evs[1].record()
+            if use_tc:
+                check(lib.spb_gram_prepare(ptr(UT), ldn, N, M, ptr(u_mean), ptr(Pf), ptr(PY3), ldn, 3, ptr(B_hi), ptr(B_lo),
+                                           ptr(g_sums), st), "spb_gram_prepare")
+                if ev_pairs is not None:
+                    evs[4].record()
+                check(lib.spb_gram_tc(ptr(A_hi), ptr(A_lo), ptr(B_hi), ptr(B_lo), ldn, N, M, 3, ptr(u_mean), ptr(g_sums),
+                                      ptr(g_scratch), g_scratch.numel(), ptr(A_d), ptr(B_d), st), "spb_gram_tc")
+            else:
+                check(lib.spb_weighted_gram(ptr(UT), ldn, N, M, ptr(Pf), ptr(PY3), ptr(A_d), ptr(B_d), st), "spb_weighted_gram")
+            if ev_pairs is not None:
+                evs[2].record()
+            # M-step on the device: (lambda sigma2 K + U^T P U) C = U^T P Y (the reference calls scipy.linalg.lstsq,
+            # sparsevfc.py:189). A Cholesky solve is the same solution whenever the system is numerically positive definite;
+            # its status flag rides along with the iteration's single host read, and the minimum-norm solution through the
+            # symmetric eigen-decomposition with lstsq's eps*M cutoff is the fallback.
             Areg = lambda_ * sigma2 * Kd + 0.5 * (A_d + A_d.T)
-            ev, Q = torch.linalg.eigh(Areg)
-            inv = torch.where(ev.abs() > rcond * ev.abs().max(), 1.0 / ev, torch.zeros_like(ev))
-            Cn = (Q * inv) @ (Q.T @ B_d)
+            L, info = torch.linalg.cholesky_ex(Areg)
+            Cn = torch.cholesky_solve(B_d, L)
             stats = torch.stack([
-                (P[:N] * Y2).sum(), (Cn * B_d).sum(), (Cn * (A_d @ Cn)).sum(), (Cn * (Kd @ Cn)).sum(),
+                (P[:N] * Y2).sum(), (Cn * B_d).sum(), (Cn * (A_d @ Cn)).sum(), (Cn * (Kd @ Cn)).sum(), info.to(torch.float64),
             ])
             s = torch.cat([sums, stats]).cpu().numpy()  # the one host synchronisation of the iteration
+            if s[9] != 0 or not np.isfinite(s[5:9]).all():
+                n_fallback += 1
+                ev, Q = torch.linalg.eigh(Areg)
+                inv = torch.where(ev.abs() > rcond * ev.abs().max(), 1.0 / ev, torch.zeros_like(ev))
+                Cn = (Q * inv) @ (Q.T @ B_d)
+                stats = torch.stack([(P[:N] * Y2).sum(), (Cn * B_d).sum(), (Cn * (A_d @ Cn)).sum(), (Cn * (Kd @ Cn)).sum()])
+                s[5:9] = stats.cpu().numpy()
+            if ev_pairs is not None:
+                evs[3].record()
+                ev_pairs.append(evs)
             E = s[0] / (2 * sigma2) + s[1] * np.log(sigma2) * D / 2 + lambda_ / 2 * reg_energy
             tecr = abs((E - E_old) / E)
             tecr_traj.append(tecr)
@@ -156,6 +207,14 @@ def SparseVFC(
             sigma2 = float(max(resid, 0.0) / (s[3] * D))
             gamma = float(min(max(s[4] / N, 0.05), 0.95))
             it += 1
+        if timings is not None:
+            torch.cuda.synchronize()
+            t = np.array([[e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])] for e in ev_pairs])
+            timings.update(estep_ms=t[:, 0], gram_ms=t[:, 1], solve_ms=t[:, 2], gram="tensor" if use_tc else "fp64",
+                           eigh_fallbacks=n_fallback)
+            if use_tc:  # split of gram_ms: operand preparation | tcgen05 contraction + fp64 fold
+                timings["gram_prepare_ms"] = np.array([e[1].elapsed_time(e[4]) for e in ev_pairs])
+                timings["gram_tc_ms"] = np.array([e[4].elapsed_time(e[2]) for e in ev_pairs])
         C = Cd[:, :D].cpu().numpy()
         # final field on the cells and on the grid
         # scratch outputs of the final evaluation are bound to names so they outlive the (asynchronous) launch

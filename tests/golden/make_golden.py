@@ -39,6 +39,9 @@ CASES = {
                              kw=dict(sparse_calculation_mode=True, sparse_top_k=48)),
     "3d_svi_sparse32": dict(n_a=1250, n_b=1200, g=20, dim=3, svi=True, max_iter=110, K=15, warp=0.0,
                             kw=dict(sparse_calculation_mode=True, sparse_top_k=32)),
+    # kernel_type="geodist" (morpho_class.py:865-871): inducing kernel from shortest paths on the kNN graph of the moving cells
+    "2d_full_geodist": dict(n_a=260, n_b=240, g=30, dim=2, svi=False, max_iter=120, K=15, warp=1.5,
+                            kw=dict(kernel_type="geodist")),
     # BASELINE configs[0]: 2-D, 5000 x 5000 cells, 100 genes, 200 iterations, the reference's default
     # SVI mode (batch 1000) and the full EM; E-step dumps at iterations 0 / 60 / 150 (5 row blocks of 1024 moving cells,
     # several column segments, zero-tile culling active at 150)

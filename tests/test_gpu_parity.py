@@ -13,6 +13,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
+from oracle import fast_host as FH  # noqa: E402
 from oracle import morpho_oracle as mo  # noqa: E402
 
 
@@ -232,7 +233,7 @@ def test_sparse_mode_edge_cases():
 
 @pytest.mark.parametrize("case", ["2d_full", "3d_full_warp", "2d_full_nonn_euc", "3d_svi", "2d_full_guide_both",
                                   "2d_svi_guide_nonrigid", "2d_full_sparse48", "3d_svi_sparse32", "c1_2d_svi",
-                                  "c1_2d_full_warp"])
+                                  "c1_2d_full_warp", "2d_full_geodist"])
 def test_full_run_matches_reference(golden, case):
     """Whole alignment through the public class: aligned coordinates within 1e-3 (relative to the coordinate range)
     of BOTH the float32 and the float64 reference runs; sigma2 / gamma close; P against the float64 reference."""
@@ -377,6 +378,8 @@ def test_error_behaviour():
         st.align.Morpho_pairwise(A, B, rep_layer="nolayer", device="0")
     with pytest.raises(NotImplementedError):
         st.align.Morpho_pairwise(A, B, kernel_type="tps", device="0")
+    with pytest.raises(NotImplementedError):  # float64 arithmetic is refused, never silently narrowed to float32
+        st.align.Morpho_pairwise(A, B, dtype="float64", device="0")
     C3, _ = make_slice_pair(60, 60, 8, dim=3)
     with pytest.raises(AssertionError):
         st.align.Morpho_pairwise(A, C3, device="0")
@@ -595,7 +598,7 @@ def test_voxel_data_device_matches_host(dim, dtype, scale):
     rng = np.random.default_rng(0)
     coords = (rng.normal(size=(3000, dim)) * np.array([1.0, 1.0, 0.2][:dim]) * scale).astype(dtype)
     exp = rng.poisson(2.0, size=(3000, 37)).astype(np.float32)
-    want_c, want_m = U.voxel_data(coords, exp, voxel_num=150)
+    want_c, want_m = FH.voxel_data(coords, exp, voxel_num=150)
     got_c, got_m = m._voxel_data_device(coords, exp, voxel_num=150)
     got_m = got_m.cpu().numpy()
     assert got_c.shape == want_c.shape and np.array_equal(got_c, want_c)

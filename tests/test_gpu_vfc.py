@@ -21,23 +21,35 @@ def _field_data(n, D, seed=0, outliers=0.1):
     return X, V
 
 
-@pytest.mark.parametrize("D,n,M", [(3, 6000, 60), (2, 4000, 33)])
-def test_sparsevfc_matches_oracle(D, n, M):
+@pytest.mark.parametrize("gram", ["fp64", "tensor"])
+@pytest.mark.parametrize("D,n,M", [(3, 6000, 60), (2, 4000, 33), (3, 20000, 300)])
+def test_sparsevfc_matches_oracle(D, n, M, gram):
+    """``gram="fp64"``: SIMT normal equations with fp64 products; ``"tensor"``: tcgen05 contraction (3xTF32) whose products
+    carry fp32-level noise — the fitted field, posterior, sigma2 and energy are compared, with a looser bar on sigma2 / E
+    for the tensor path (sigma2 is a difference of large sums of those products)."""
     from spateo_release_b200.tdr.sparsevfc import SparseVFC
 
     X, V = _field_data(n, D)
     ctrl_idx = np.random.default_rng(1).permutation(n)[:M]
     beta = 1.0 / 25.0**2
     grid = X[:50] + 0.5
-    got = SparseVFC(X, V, Grid=grid, M=M, beta=beta, lambda_=0.02, MaxIter=40, ecr=0.0, ctrl_idx=ctrl_idx, device="0")
+    tm = {}
+    got = SparseVFC(X, V, Grid=grid, M=M, beta=beta, lambda_=0.02, MaxIter=40, ecr=0.0, ctrl_idx=ctrl_idx, device="0",
+                    gram=gram, timings=tm)
     want = mo.sparse_vfc(X, V, ctrl_idx, beta, lambda_=0.02, MaxIter=40, ecr=0.0, Grid=grid)
-    assert got["iteration"] == want["iteration"] - 1
+    assert got["iteration"] == want["iteration"] - 1 and tm["gram"] == gram
     scale = np.abs(want["V"]).max()
-    assert np.abs(got["V"] - want["V"]).max() < 1e-4 * scale
-    assert np.abs(got["grid_V"] - want["grid_V"]).max() < 1e-4 * scale
-    assert abs(got["sigma2"] - want["sigma2"]) < 1e-4 * want["sigma2"]
-    assert np.abs(got["P"][:, 0] - want["P"]).max() < 1e-3
-    assert np.abs(got["E_traj"] - want["E_traj"]).max() < 1e-5 * np.abs(want["E_traj"]).max()
+    eV = np.abs(got["V"] - want["V"]).max() / scale
+    eS = abs(got["sigma2"] - want["sigma2"]) / want["sigma2"]
+    eE = np.abs(got["E_traj"] - want["E_traj"]).max() / np.abs(want["E_traj"]).max()
+    print(f"\n[vfc {gram} D={D} n={n} M={M}] V {eV:.2e}  sigma2 {eS:.2e}  E {eE:.2e}  P {np.abs(got['P'][:, 0] - want['P']).max():.2e}"
+          f"  eigh fallbacks {tm['eigh_fallbacks']}")
+    loose = gram == "tensor"
+    assert eV < (5e-4 if loose else 1e-4)
+    assert np.abs(got["grid_V"] - want["grid_V"]).max() < (5e-4 if loose else 1e-4) * scale
+    assert eS < (2e-3 if loose else 1e-4)
+    assert np.abs(got["P"][:, 0] - want["P"]).max() < (5e-3 if loose else 1e-3)
+    assert eE < (1e-3 if loose else 1e-5)
     assert set(["X", "valid_ind", "X_ctrl", "ctrl_idx", "Y", "beta", "V", "C", "P", "VFCIndex", "sigma2", "grid", "grid_V",
                 "iteration", "tecr_traj", "E_traj"]) <= set(got)
     # outliers are recognised

