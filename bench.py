@@ -59,8 +59,11 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary EM-loop timings (default SVI mode; K=200 inducing points) of SURVEY.md 8(d) config 2")
-    ap.add_argument("--workload", default="pair", choices=["pair", "vfc"],
-                    help="pair = BASELINE configs[1] (headline); vfc = configs[4] SparseVFC (secondary line)")
+    ap.add_argument("--workload", default="pair", choices=["pair", "vfc", "chain", "shard"],
+                    help="pair = BASELINE configs[1] (headline); vfc = configs[4] SparseVFC; chain = configs[2] (16-slice chain "
+                         "sharded over the GPUs, torchrun); shard = ONE pair column-sharded over the GPUs (strong scaling)")
+    ap.add_argument("--chain-slices", type=int, default=16)
+    ap.add_argument("--chain-cells", type=int, default=50000)
     ap.add_argument("--vfc-cells", type=int, default=1000000)
     ap.add_argument("--vfc-M", type=int, default=500)
     ap.add_argument("--vfc-iters", type=int, default=50)
@@ -353,6 +356,217 @@ def run_vfc(args):
     }), flush=True)
 
 
+def make_chain_slice(k, n, G, device):
+    """Slice k of a synthetic serial-section chain: the same 2-D tissue (smooth expression programmes) re-sampled with its own
+    cells and counts, placed with its own pose (rotation 0.12 k rad, translation (3 k, -2 k)) plus 0.3 positional jitter."""
+    import pandas as pd
+    import torch
+
+    from spateo_release_b200.anndata_lite import AnnDataLite
+
+    g0 = torch.Generator(device=device)
+    g0.manual_seed(4321)  # shared programmes
+    W = torch.randn((2, G), generator=g0, device=device, dtype=torch.float64)
+    phi = torch.rand((G,), generator=g0, device=device, dtype=torch.float64) * 2 * np.pi
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 + k)
+    base = torch.rand((n, 2), generator=g, device=device, dtype=torch.float64) * 100
+    lam = torch.exp(torch.sin(base @ W / 30.0 + phi)).float()
+    X = torch.poisson(lam, generator=g)
+    th = 0.12 * k
+    R = torch.tensor([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]], dtype=torch.float64, device=device)
+    tvec = torch.tensor([3.0 * k, -2.0 * k], dtype=torch.float64, device=device)
+    coords = base @ R.T + tvec + torch.randn((n, 2), generator=g, device=device, dtype=torch.float64) * 0.3
+    var = pd.DataFrame(index=[f"g{i}" for i in range(G)])
+    ad = AnnDataLite(X.cpu().numpy(), var=var, obsm={"spatial": coords.cpu().numpy()})
+    ad.uns["pose"] = (th, 3.0 * k, -2.0 * k)
+    ad.uns["base"] = base.cpu().numpy()
+    return ad
+
+
+def run_chain(args):
+    """BASELINE configs[2]: serial chain of ``--chain-slices`` 2-D slices x ``--chain-cells`` cells x ``--genes`` genes;
+    consecutive pairs are independent problems sharded round-robin over the ranks (pair p -> rank p mod N), each rank
+    software-pipelines its pairs (host preparation + H2D of the next pair under the EM of the current one), ONE NCCL
+    all-gather of the 2-D similarities, prefix composition, every rank places its own slices.
+    value = (pairs x N_A x N_B x iterations) / max-over-ranks wall time of the whole job, host arrays in / host arrays out."""
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import spateo_release_b200 as st
+    from spateo_release_b200.alignment.distributed import align_chain_pipelined, shard_pairs
+
+    S, n, G = args.chain_slices, args.chain_cells, args.genes
+    n_pairs = S - 1
+    mine = shard_pairs(n_pairs, rank, world)
+    need = sorted({q for p in mine for q in (p, p + 1)})
+    slices = {k: make_chain_slice(k, n, G, dev) for k in need}  # untimed: stands for the slices on this rank's disk
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    kw = dict(SVI_mode=bool(args.svi), max_iter=args.max_iter, K=args.K, nn_init=True, verbose=False)
+    times, stats = [], {}
+    sampler = ClockSampler(local_rank)
+    n_run = args.warmup + args.steps
+    for s in range(n_run):
+        for ad in slices.values():
+            ad.obsm.pop("align_spatial", None)
+        if s == args.warmup:
+            sampler.start()
+        barrier()
+        t0 = time.perf_counter()
+        np.random.seed(rank)
+        stats = {}
+        placed, tr = align_chain_pipelined(lambda k: slices[k], S, device=str(local_rank), stats=stats, **kw)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(max_over_ranks(dt))
+    clocks = sampler.stop()
+    # sanity: every placed slice lands on the frame of slice 0 (residual against the common tissue coordinates)
+    res = 0.0
+    for k, ad in placed.items():
+        want = ad.uns["base"]  # slice 0 carries the identity pose: its frame is the tissue's own
+        res = max(res, float(np.sqrt(np.mean(np.sum((np.asarray(ad.obsm["align_spatial"]) - want) ** 2, axis=1)))))
+    res = max_over_ranks(res)
+    sec = float(np.mean(times))
+    pairs_per_iter = float(n) * (args.chain_cells // 10 if args.svi else n)
+    total = float(n_pairs) * pairs_per_iter * args.max_iter
+    busiest = max(len(shard_pairs(n_pairs, r, world)) for r in range(world))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "cell-pairs/sec through morpho_align EM (slice chain)", "value": total / sec, "unit": "cell-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"chain of {S} 2-D slices x {n} cells x {G} genes = {n_pairs} independent pairs (KL, "
+                                   f"{'SVI' if args.svi else 'full EM'}, K={args.K}, max_iter={args.max_iter}) round-robin over "
+                                   f"{world} GPU(s), next pair prepared under the current pair's EM, 1 all-gather, prefix composition",
+                       "pairs_on_busiest_gpu": busiest, "load_balance_ceiling": n_pairs / float(busiest * world),
+                       "cache": "inputs_larger_than_L2 (cost matrix %.1f GB per pair)" % (4.0 * n * n / 1e9)},
+            "clocks": clocks,
+            "e2e": {"value": total / sec, "unit": "cell-pairs/s", "h2d_bytes_per_step": int(busiest * 2 * n * G * 4),
+                    "d2h_bytes_per_step": int(busiest * n * 2 * 4 * 4),
+                    "note": "value is end to end by construction: host arrays in, placed coordinates out, per rank"},
+            "gpu_launches": int(stats.get("kernel_launches", 0)),
+            "chain": {"seconds_per_pair_rank0": stats.get("seconds_per_pair"), "rms_residual_vs_truth": res,
+                      "pairs": n_pairs, "pairs_rank0": stats.get("pairs")},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_shard(args):
+    """ONE slice pair (BASELINE configs[1] shape) column-sharded over the ranks: strong scaling of a single alignment. Every
+    rank holds the moving slice and N_B / world fixed cells; per iteration the only exchange is the sum of 7 fp64 row
+    statistics per moving cell, done inside the row-finalize kernel over NVLink peer memory (mode p2p) or by ncclAllReduce.
+    value = N_A x N_B x iterations / max-over-ranks device time of the EM loop (cost matrix blocks resident)."""
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from spateo_release_b200.alignment.distributed import morpho_align_pair_sharded
+
+    A, B = make_pair_on_device(args.cells, args.genes, args.dim, seed=0, device=dev)  # the SAME pair on every rank
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    results = {}
+    clocks = None
+    for mode in (["p2p", "nccl"] if world > 1 else ["nccl"]):
+        np.random.seed(0)
+        t0 = time.perf_counter()
+        try:
+            m = morpho_align_pair_sharded(A, B, mode=mode, device=str(local_rank), max_iter=args.max_iter, K=args.K, nn_init=True,
+                                          verbose=False)
+        except Exception as e:  # symmetric memory unavailable: report and continue with the collective
+            results[mode] = {"unavailable": repr(e)[:300]}
+            continue
+        barrier()
+        t_prep = time.perf_counter() - t0
+        ms = []
+        sampler = ClockSampler(local_rank)
+        for s in range(args.warmup + args.steps):
+            m.reset_state()
+            if s == args.warmup and mode != "nccl" or (s == args.warmup and world == 1):
+                sampler.start()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m.run_em()
+            e1.record()
+            barrier()
+            if s >= args.warmup:
+                ms.append(max_over_ranks(e0.elapsed_time(e1)))
+        if sampler.proc is not None:
+            clocks = sampler.stop()
+        m._finish()
+        results[mode] = {"ms_per_step": float(np.mean(ms)), "mode_used": m._shard_mode, "prepare_s": max_over_ranks(t_prep),
+                         "sigma2_final": float(m.sigma2), "checksum_XAHat": float(np.abs(m.XAHat).sum())}
+        del m
+        torch.cuda.empty_cache()
+    if rank == 0:
+        best = min((v for v in results.values() if "ms_per_step" in v), key=lambda v: v["ms_per_step"])
+        pairs = float(args.cells) * args.cells * args.max_iter
+        print(json.dumps({
+            "metric": "cell-pairs/sec through morpho_align EM (one pair, column-sharded)", "value": pairs / (best["ms_per_step"] * 1e-3),
+            "unit": "cell-pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"ONE morpho_align pair, {args.cells} x {args.cells} cells, {args.genes} genes, {args.dim}-D, full "
+                                   f"EM, K={args.K}, max_iter={args.max_iter}; fixed cells split over {world} GPU(s), row statistics "
+                                   "summed once per iteration (7 fp64 per moving cell)",
+                       "cache": "inputs_larger_than_L2 (cost-matrix block %.1f GB per GPU)" % (4.0 * args.cells * args.cells / world / 1e9)},
+            "clocks": clocks, "modes": results,
+            "e2e": None, "gpu_launches": None,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -360,6 +574,12 @@ def main():
         return
     if args.workload == "vfc":
         run_vfc(args)
+        return
+    if args.workload == "chain":
+        run_chain(args)
+        return
+    if args.workload == "shard":
+        run_shard(args)
         return
     import torch
     import torch.distributed as dist

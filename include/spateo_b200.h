@@ -93,7 +93,7 @@ typedef struct spb_em_params {
   int32_t g_rigid;             /* guidance_effect in ("rigid", "both") */
   int32_t g_NI;                /* number of guidance pairs */
   int32_t sparse_k;            /* > 0: sparse_calculation_mode with sparse_top_k = sparse_k (utils.py:1085-1094) */
-  int32_t reserved0;
+  int32_t NB_total;            /* column-sharded pair: fixed cells of ALL ranks (gamma update); 0 = NBb */
   int32_t reserved1;
   double lambdaVF;
   double gamma_a;
@@ -160,6 +160,17 @@ typedef struct spb_em_params {
   const double* g_G1;          /* [K][K] U_I^T U_I */
   spb_scalars* sc;             /* device scalars */
   double* trace_buf;           /* [max_iter][SPB_TRACE_STRIDE] or NULL */
+  double* red_scratch;         /* [red_scratch_doubles] block partials of the deterministic (ordered) grid reductions */
+  int64_t red_scratch_doubles;
+  uint32_t* red_counter;       /* [8] arrival tickets of those reductions (zero-initialised) */
+  /* column-sharded pair (one slice pair over several GPUs): every rank holds a block of fixed cells */
+  /* (columns of P); sweep 1 is local, the per-row statistics of sweep 2 are summed over the ranks once per iteration */
+  int32_t shard_rank;
+  int32_t shard_world;         /* 0 / 1 = not sharded */
+  double* rowstat;             /* [2][8][ldx] fp64 row statistics of THIS rank's columns, double-buffered by call parity */
+  const uint64_t* peer_rowstat; /* device array [shard_world]: every rank's rowstat base mapped into this process (NVLink P2P), or NULL */
+  uint64_t* shard_flags;       /* [shard_world] epochs written by the peers (this rank's own slot by itself) */
+  const uint64_t* peer_flags;  /* device array [shard_world]: every rank's shard_flags base, P2P mapped */
 } spb_em_params;
 
 /* ---- library info ------------------------------------------------------------------------------------------- */
@@ -219,6 +230,13 @@ int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream); /* uti
 int spb_col_finalize(const spb_em_params* p, void* stream);               /* utils.py:1053-1055 + denominators */
 int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream); /* utils.py:1059-1083, morpho_class.py:1171-1176,1270,1357 */
 int spb_row_finalize(const spb_em_params* p, void* stream);
+/* column-sharded pair: (1) fold this rank's segment partials into rowstat[parity] (fp64); (2a) after the caller summed
+   rowstat[parity] over the ranks (e.g. ncclAllReduce), finish the row statistics from it; or (2b) ONE kernel that signals
+   the peers, waits for their epoch flags and sums their rowstat[parity] straight over NVLink peer memory in rank order
+   (bit-identical on every rank) before finishing — no separate collective. epoch must increase by one per call on every rank. */
+int spb_row_fold(const spb_em_params* p, int32_t parity, void* stream);
+int spb_row_stats_finalize(const spb_em_params* p, int32_t parity, void* stream);
+int spb_row_stats_p2p(const spb_em_params* p, int32_t parity, uint64_t epoch, void* stream);
 /* dense P [NA][NBb] (row-major, pitch ldp) of the state left by the last E-step */
 /* sparse_calculation_mode (p->sparse_k > 0): per-column top-k threshold tau_j of the full posterior by an exact radix
    select (one CTA per column), written to colconst[j][18..19]; K_NB_j becomes the kept mass. Call between
@@ -250,6 +268,8 @@ int spb_em_iteration(const spb_em_params* p, int32_t iter, void* stream);    /* 
    spb_scalars.iter + 1 (SVI batch, step size, the iter < 100 sigma2 floor and the trace row all follow it), so ONE captured
    CUDA graph of this call replays every iteration of a phase */
 int spb_em_iteration_ex(const spb_em_params* p, int32_t iter, int32_t nonrigid, void* stream);
+/* one-time per-device kernel attributes of the non-rigid phase (lets the phase be graph-captured before its first eager launch) */
+int spb_nonrigid_warm(void);
 /* closing similarity from the last E-step's statistics: out = optimal_R[9], optimal_t[3] (device doubles) */
 int spb_optimal_rigid(const spb_em_params* p, double* out12, void* stream);  /* morpho_class.py:1451-1468 */
 

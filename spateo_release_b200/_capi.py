@@ -20,6 +20,7 @@ _SCALAR_TYPES = {
     "int32_t": C.c_int32,
     "uint32_t": C.c_uint32,
     "int64_t": C.c_int64,
+    "uint64_t": C.c_uint64,
     "float": C.c_float,
     "double": C.c_double,
 }
@@ -127,6 +128,9 @@ def load_library():
         "spb_col_finalize": ([EP, P], C.c_int),
         "spb_estep_sweep2": ([EP, I32, P], C.c_int),
         "spb_row_finalize": ([EP, P], C.c_int),
+        "spb_row_fold": ([EP, I32, P], C.c_int),
+        "spb_row_stats_finalize": ([EP, I32, P], C.c_int),
+        "spb_row_stats_p2p": ([EP, I32, C.c_uint64, P], C.c_int),
         "spb_estep_col_select": ([EP, I32, P], C.c_int),
         "spb_sparse_P_emit": ([EP, I32, P, P, P], C.c_int),
         "spb_posterior_argmax": ([EP, I32, P, P, P], C.c_int),
@@ -142,6 +146,7 @@ def load_library():
         "spb_row_update": ([EP, P], C.c_int),
         "spb_em_iteration": ([EP, I32, P], C.c_int),
         "spb_em_iteration_ex": ([EP, I32, I32, P], C.c_int),
+        "spb_nonrigid_warm": ([], C.c_int),
         "spb_optimal_rigid": ([EP, P, P], C.c_int),
         "spb_rbf_kernel_T": ([P, I64, I64, P, I32, F, P, P], C.c_int),
         "spb_field_eval": ([P, I64, I32, P, P, I32, D, P, P], C.c_int),

@@ -55,6 +55,7 @@ def _count_d2h(t) -> None:
 
 _STAGE_FLOATS = 16 << 20  # two reusable 64 MB pinned staging buffers
 _stage = {}
+_stage_lock = __import__("threading").Lock()
 
 
 def staged_to_device(host: np.ndarray, dev: torch.device) -> torch.Tensor:
@@ -66,14 +67,14 @@ def staged_to_device(host: np.ndarray, dev: torch.device) -> torch.Tensor:
     _count_h2d(t)
     if t.is_pinned() or t.numel() < (2 << 20):
         return t.to(dev, non_blocking=t.is_pinned())
-    if "bufs" not in _stage:
-        _stage["bufs"] = [torch.empty((_STAGE_FLOATS,), dtype=torch.float32).pin_memory() for _ in range(2)]
-    bufs = _stage["bufs"]
     events = [torch.cuda.Event(), torch.cuda.Event()]
     out = torch.empty(t.shape, dtype=torch.float32, device=dev)
     src, dst = t.view(-1), out.view(-1)
     n = src.numel()
-    with torch.cuda.device(dev):
+    with _stage_lock, torch.cuda.device(dev):
+        if "bufs" not in _stage:
+            _stage["bufs"] = [torch.empty((_STAGE_FLOATS,), dtype=torch.float32).pin_memory() for _ in range(2)]
+        bufs = _stage["bufs"]
         for k, o in enumerate(range(0, n, _STAGE_FLOATS)):
             b = k & 1
             m = min(_STAGE_FLOATS, n - o)
@@ -247,6 +248,7 @@ class Morpho_pairwise:
     ``spatial_sort`` / ``cull_zero_tiles`` — the moving cells are processed in Morton order so that each 1024-row block is
     spatially compact, and (row block, fixed cell) tiles whose every pair underflows to exactly 0 in fp32 are skipped;
     results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
+    ``column_shard`` — set by ``morpho_align_pair_sharded``: one pair's fixed cells split over several GPUs.
     Accepted but without effect (memory work-arounds whose results are identical): ``use_chunk``, ``chunk_capacity``,
     ``pre_compute_dist``. ``sparse_calculation_mode`` keeps the top ``sparse_top_k`` posterior entries of every column by an
     exact on-device radix select (P comes back as ``scipy.sparse.coo_matrix``). Not implemented (NotImplementedError):
@@ -314,6 +316,7 @@ class Morpho_pairwise:
         compute_mapping: bool = False,
         spatial_sort: bool = True,
         cull_zero_tiles: bool = True,
+        column_shard=None,
     ) -> None:
         self.verbose = verbose
         self.sampleA, self.sampleB = sampleA, sampleB
@@ -347,6 +350,9 @@ class Morpho_pairwise:
         self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
         self.use_cuda_graph = os.environ.get("SPB_CUDA_GRAPH", "1") != "0"
+        # column-sharded pair: (rank, world, mode) — this process holds the fixed cells [NB * rank / world, NB * (rank + 1) /
+        # world) of ONE pair; see alignment/distributed.py:morpho_align_pair_sharded
+        self.column_shard = column_shard
 
         self._np_dtype = np.float32 if dtype == "float32" else np.float64
         self._check()
@@ -812,7 +818,9 @@ class Morpho_pairwise:
         """GT[j][i] = prod_layers prob(metric(A_i, B_j)) (morpho_class.py:265-268 + utils.py:1080-1081)."""
         dev, lib = self._dev, self._lib
         self._set_row_order()
-        self._GT = torch.empty((self.NB, self.ldx), dtype=torch.float32, device=dev)
+        c0, c1 = self._col_range()
+        nb_loc = c1 - c0
+        self._GT = torch.empty((nb_loc, self.ldx), dtype=torch.float32, device=dev)
         gc = GeneCostBuilder(lib, dev)
         first = True
         for eA, eB, d_s, p_t, p_p in zip(
@@ -820,10 +828,10 @@ class Morpho_pairwise:
         ):
             if d_s == "label":
                 la = torch.from_numpy(np.ascontiguousarray(eA if self._perm is None else eA[self._perm], dtype=np.int32)).to(dev)
-                lb = torch.from_numpy(np.ascontiguousarray(eB, dtype=np.int32)).to(dev)
+                lb = torch.from_numpy(np.ascontiguousarray(eB[c0:c1], dtype=np.int32)).to(dev)
                 LT = torch.from_numpy(np.ascontiguousarray(self.label_transfer, dtype=np.float32)).to(dev)
                 check(
-                    lib.spb_label_cost(ptr(la), ptr(lb), ptr(LT), LT.shape[1], self.NA, self.NB, 0 if first else 1,
+                    lib.spb_label_cost(ptr(la), ptr(lb), ptr(LT), LT.shape[1], self.NA, nb_loc, 0 if first else 1,
                                        ptr(self._GT), self.ldx, _capi.current_stream_ptr()),
                     "spb_label_cost",
                 )
@@ -831,12 +839,19 @@ class Morpho_pairwise:
                 A = self._to_device_pinned(eA)
                 if self._perm is not None:
                     A = A.index_select(0, self._perm_dev)  # moving cells in Morton order
-                B = self._to_device_pinned(eB)
+                B = self._to_device_pinned(eB) if self.column_shard is None else staged_to_device(eB[c0:c1], dev)
                 opA, rtA, opB, rtB, G_eff = gc.prepare_pair(A, B, d_s)
-                gc.cost(opA, rtA, opB, rtB, self.NA, self.NB, G_eff, d_s, p_t, p_p, not first, self._GT, self.ldx)
+                gc.cost(opA, rtA, opB, rtB, self.NA, nb_loc, G_eff, d_s, p_t, p_p, not first, self._GT, self.ldx)
                 del A, B, opA, opB
             first = False
         self.__dict__.pop("_dev_rep", None)  # the resident copies of the representations are no longer needed
+
+    def _col_range(self):
+        """Fixed cells (columns of P) held by this process: all of them, or this rank's block of a column-sharded pair."""
+        if self.column_shard is None:
+            return 0, self.NB
+        r, w = int(self.column_shard[0]), int(self.column_shard[1])
+        return (self.NB * r) // w, (self.NB * (r + 1)) // w
 
     def _to_device_pinned(self, host_array: np.ndarray) -> torch.Tensor:
         """Device copy of one dense representation, uploaded ONCE per preparation (the coarse initialisation, the beta^2
@@ -891,8 +906,14 @@ class Morpho_pairwise:
         return seg
 
     def _allocate_state(self):
-        dev, D, NA, NB, K, ldx = self._dev, self.D, self.NA, self.NB, self.K, self.ldx
+        dev, D, NA, K, ldx = self._dev, self.D, self.NA, self.K, self.ldx
         f32, f64 = torch.float32, torch.float64
+        c0, c1 = self._col_range()
+        NB = c1 - c0  # columns held by this process (all of them unless the pair is column-sharded)
+        if self.column_shard is not None and (self.SVI_mode or self.sparse_calculation_mode or self.guidance or self.materialize_P
+                                              or self.compute_mapping or self.return_mapping):
+            raise NotImplementedError("a column-sharded pair supports the full EM only (SVI_mode=False, materialize_P=False, no "
+                                      "sparse mode / guidance / mapping outputs)")
         nbb = self.batch_size if self.SVI_mode else NB
         nbb_alloc = NB if (self.return_mapping and self.SVI_mode) else nbb
         self._NBb = nbb
@@ -902,7 +923,7 @@ class Morpho_pairwise:
         s["xa"] = torch.zeros((3, ldx), dtype=f32, device=dev)
         s["xa"][:D, :NA] = torch.from_numpy(np.ascontiguousarray(self._sorted(self.coordsA).T, dtype=np.float32)).to(dev)
         s["xb4"] = torch.zeros((NB, 4), dtype=f32, device=dev)
-        s["xb4"][:, :D] = torch.from_numpy(self.coordsB.astype(np.float32)).to(dev)
+        s["xb4"][:, :D] = torch.from_numpy(self.coordsB[c0:c1].astype(np.float32)).to(dev)
         s["Gamma"] = torch.from_numpy(np.ascontiguousarray(self.GammaSparse, dtype=np.float32)).to(dev)
         s["kappa"] = torch.ones((ldx,), dtype=f32, device=dev)
         s["kappa"][:NA] = torch.from_numpy(self._sorted(self.kappa).astype(np.float32)).to(dev)
@@ -969,6 +990,16 @@ class Morpho_pairwise:
         # params
         p = SpbEmParams()
         p.NA, p.NB, p.NBb, p.D, p.K, p.ldx = NA, NB, nbb, D, K, ldx
+        p.NB_total = self.NB if self.column_shard is not None else 0
+        # block partials + tickets of the ordered (reproducible) grid reductions
+        n_red = max(592 * 29, ((NA + 255) // 256) * 4, 320 * K * (K + 3) if K <= 32 else 0) + 64
+        s["red_scratch"] = torch.zeros((n_red,), dtype=f64, device=dev)
+        s["red_counter"] = torch.zeros((8,), dtype=torch.int32, device=dev)
+        p.red_scratch, p.red_scratch_doubles, p.red_counter = s["red_scratch"].data_ptr(), n_red, s["red_counter"].data_ptr()
+        p.shard_rank = p.shard_world = 0
+        p.rowstat = p.peer_rowstat = p.shard_flags = p.peer_flags = None
+        if self.column_shard is not None:
+            self._setup_column_shard(p, s)
         p.svi, p.nn_init, p.update_R = int(self.SVI_mode), int(self.nn_init), int(self.update_R)
         p.nonrigid_start_iter = int(self.nonrigid_start_iter)
         p.seg1, p.seg2, p.nbb_pad, p.trace = seg1, seg2, self._nbb_pad, 1
@@ -1046,6 +1077,67 @@ class Morpho_pairwise:
             p.gram_scratch_floats = 0
         self._params = p
 
+    def _setup_column_shard(self, p, s):
+        """Buffers of the column-sharded pair: fp64 row statistics of this rank's columns (double-buffered) + epoch flags.
+        ``mode`` "p2p" (default when available): the buffer is symmetric memory, every rank maps every peer's copy and the
+        row-finalize kernel sums them straight over NVLink; "nccl": plain buffer + ``all_reduce`` (the baseline)."""
+        import torch.distributed as dist
+
+        rank, world = int(self.column_shard[0]), int(self.column_shard[1])
+        mode = self.column_shard[2] if len(self.column_shard) > 2 else "auto"
+        dev, ldx = self._dev, self.ldx
+        n_stat = 2 * 8 * ldx
+        p.shard_rank, p.shard_world = rank, world
+        self._shard_epoch = 0
+        self._shard_mode = "nccl"
+        buf = None
+        if mode in ("auto", "p2p") and world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                buf = symm.empty((n_stat + 64,), dtype=torch.float64, device=dev)
+                buf.zero_()
+                try:
+                    hdl = symm.rendezvous(buf, dist.group.WORLD.group_name)
+                except Exception:
+                    hdl = symm.rendezvous(buf, dist.group.WORLD)
+                ptrs = [int(q) for q in hdl.buffer_ptrs]
+                s["shard_hdl"] = hdl
+                s["peer_rowstat"] = torch.tensor(ptrs, dtype=torch.int64, device=dev)
+                s["peer_flags"] = torch.tensor([q + n_stat * 8 for q in ptrs], dtype=torch.int64, device=dev)
+                p.peer_rowstat, p.peer_flags = s["peer_rowstat"].data_ptr(), s["peer_flags"].data_ptr()
+                self._shard_mode = "p2p"
+                hdl.barrier()
+            except Exception as e:  # no symmetric memory on this system: fall back to the collective
+                if mode == "p2p":
+                    raise
+                buf = None
+                self._shard_fallback_reason = repr(e)
+        if buf is None:
+            buf = torch.zeros((n_stat + 64,), dtype=torch.float64, device=dev)
+        s["rowstat"] = buf
+        p.rowstat = buf.data_ptr()
+        p.shard_flags = buf.data_ptr() + n_stat * 8
+
+    def _shard_row_statistics(self, st):
+        """Row statistics of a column-sharded pair: local fold, sum over the ranks, finish (replaces spb_row_finalize)."""
+        import torch.distributed as dist
+
+        lib, p, s = self._lib, self._params, self._state
+        parity = self._shard_epoch & 1
+        self._shard_epoch += 1
+        check(lib.spb_row_fold(C.byref(p), parity, st), "spb_row_fold")
+        if self._shard_mode == "p2p":
+            check(lib.spb_row_stats_p2p(C.byref(p), parity, self._shard_epoch, st), "spb_row_stats_p2p")
+        else:
+            view = s["rowstat"][parity * 8 * self.ldx : (parity + 1) * 8 * self.ldx]
+            hook = getattr(self, "_shard_reduce_hook", None)
+            if hook is not None:  # tests: several shards stepped in lock-step inside one process
+                hook(self, view)
+            elif dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(view)
+            check(lib.spb_row_stats_finalize(C.byref(p), parity, st), "spb_row_stats_finalize")
+
     def _read_scalars(self) -> SpbScalars:
         raw = self._state["sc"].cpu().numpy().tobytes()
         return SpbScalars.from_buffer_copy(raw)
@@ -1081,7 +1173,7 @@ class Morpho_pairwise:
         lib, p = self._lib, self._params
         nonrigid = it > self.nonrigid_start_iter
         large_K = nonrigid and self.K > _capi.MAX_K_FUSED
-        if not (large_K or capture_P or sweep_events is not None):
+        if not (large_K or capture_P or sweep_events is not None or self.column_shard is not None):
             check(lib.spb_em_iteration(C.byref(p), it, st), "spb_em_iteration")
             return
         self._estep_only(it, st, sweep_events)
@@ -1155,7 +1247,10 @@ class Morpho_pairwise:
         if sweep_events is not None:
             e3.record()
             sweep_events.append((e0, e1, e2, e3))
-        check(lib.spb_row_finalize(C.byref(p), st), "spb_row_finalize")
+        if self.column_shard is not None:
+            self._shard_row_statistics(st)
+        else:
+            check(lib.spb_row_finalize(C.byref(p), st), "spb_row_finalize")
 
     def prepare_host(self):
         """Coarse rigid initialisation + variational initialisation (host numpy with small device helpers); consumes
@@ -1168,11 +1263,12 @@ class Morpho_pairwise:
             if self.nn_init:
                 with _nvtx("coarse_rigid_alignment"):
                     self._coarse_rigid_alignment()
-            torch.cuda.synchronize()
+            # (stream-level waits: a second pair may be running its EM on another stream of this device)
+            torch.cuda.current_stream().synchronize()
             self._timing["coarse_rigid_alignment_s"] = _time.perf_counter() - t0
             t0 = _time.perf_counter()
             self._initialize_variational_variables()
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             self._timing["variational_init_s"] = _time.perf_counter() - t0
         self._host_ready = True
 
@@ -1218,7 +1314,7 @@ class Morpho_pairwise:
                 last = it == self.max_iter - 1
                 want_P = (self.materialize_P or self.compute_mapping) and last and not (self.return_mapping and self.SVI_mode)
                 nonrigid = it > self.nonrigid_start_iter
-                plain = (hist is not None or sweep_events is not None or want_P or _nvtx.enabled
+                plain = (hist is not None or sweep_events is not None or want_P or _nvtx.enabled or self.column_shard is not None
                          or not getattr(self, "use_cuda_graph", True) or (nonrigid and self.K > _capi.MAX_K_FUSED))
                 if not plain:
                     # iterations [it, stop) share the phase and need nothing from the host
@@ -1227,6 +1323,11 @@ class Morpho_pairwise:
                         stop -= 1  # the last iteration captures the posterior: plain path
                     if stop - it >= 3:
                         self._iteration(it, st)  # explicit index: also the warm-up launch of every kernel of the phase
+                        if not nonrigid and end > self.nonrigid_start_iter + 4 and self.K <= _capi.MAX_K_FUSED:
+                            # capture the graph of the later non-rigid phase now as well: a capture synchronises the
+                            # device, and doing it here keeps the host free to enqueue the whole run without stopping
+                            check(self._lib.spb_nonrigid_warm(), "spb_nonrigid_warm")
+                            self._iteration_graph(True)
                         graph, n_kernels = self._iteration_graph(nonrigid)
                         for _ in range(it + 1, stop):
                             graph.replay()
@@ -1326,6 +1427,18 @@ class Morpho_pairwise:
         self.optimal_RnA = (self.coordsA.astype(np.float64) @ self.optimal_R.astype(np.float64).T + self.optimal_t).astype(dt)
         self.K_NA = vec("K_NA")
         self.K_NB = s["K_NB"][: self._NBb].cpu().numpy().astype(dt)
+        if self.column_shard is not None:  # every rank holds the column sums of its own block of fixed cells
+            import torch.distributed as dist
+
+            if dist.is_initialized() and dist.get_world_size() > 1:
+                world = dist.get_world_size()
+                width = (self.NB + world - 1) // world + 1
+                mine = torch.zeros((width,), dtype=torch.float32, device=self._dev)
+                mine[: self._NBb] = s["K_NB"][: self._NBb]
+                parts = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(parts, mine)
+                sizes = [(self.NB * (r + 1)) // world - (self.NB * r) // world for r in range(world)]
+                self.K_NB = np.concatenate([q[:n].cpu().numpy() for q, n in zip(parts, sizes)]).astype(dt)
         self.K_NA_spatial = vec("K_NA_spatial")
         self.K_NA_sigma2 = vec("K_NA_sigma2")
         self.alpha = vec("alpha")

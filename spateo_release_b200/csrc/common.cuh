@@ -11,6 +11,7 @@
 #define SPB_STAGES 3
 
 extern "C" int64_t spb_launch_count(void);
+int spb_gram_tc_warm();  // gram_tc.cu
 void spb_count_launch(int n = 1);
 
 // kernel attributes (dynamic shared-memory opt-in) are per device: index the "already set" flags by the current device
@@ -115,6 +116,47 @@ __device__ __forceinline__ void block_reduce_atomic(double (&v)[NV], double* dst
     }
   }
   __syncthreads();
+}
+
+// Deterministic grid-wide sum of NV doubles per block: every block stores its block-reduced partials, the LAST block to
+// arrive (atomic ticket) adds the gridDim.x partials of each value in a fixed order and writes (or adds to) dst. Unlike
+// block_reduce_atomic the result does not depend on block scheduling, so replicas of the EM on several GPUs stay bit-identical
+// (column-sharded pair) and runs are reproducible. partials: [gridDim.x][NV]; counter: zero before the first use (it is
+// reset by the last block). blockDim.x multiple of 32, <= 1024.
+template <int NV>
+__device__ __forceinline__ void grid_reduce_ordered(double (&v)[NV], double* __restrict__ partials, unsigned int* counter,
+                                                    double* dst, bool accumulate) {
+  __shared__ double red_[32][NV];
+  __shared__ bool is_last_;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int q = 0; q < NV; ++q) v[q] = warp_sum(v[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) red_[warp][q] = v[q];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+      double x = lane < nw ? red_[lane][q] : 0.0;
+      x = warp_sum(x);
+      if (lane == 0) partials[(size_t)blockIdx.x * NV + q] = x;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last_ = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last_) return;
+  __threadfence();
+  for (int q = warp; q < NV; q += nw) {
+    double x = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) x += partials[(size_t)b * NV + q];
+    x = warp_sum(x);
+    if (lane == 0) dst[q] = accumulate ? dst[q] + x : x;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

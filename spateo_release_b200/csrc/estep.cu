@@ -441,11 +441,24 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   A.store(rowpart + ((int64_t)seg * 8) * ldx + r, ldx);
 }
 
-// per row: fold the segment partials (fp64), write the fp32 statistics, accumulate the global sums
-__global__ void row_finalize_kernel(const float* __restrict__ rowpart, int nseg, int ldx, int NA,
-                                    const float* __restrict__ mm, float* __restrict__ K_NA_spatial,
-                                    float* __restrict__ K_NA_sigma2, float* __restrict__ K_NA, float* __restrict__ PXB,
-                                    spb_scalars* sc) {
+// per row: fold the segment partials (fp64), write the fp32 statistics, accumulate the global sums (ordered: reproducible)
+__device__ __forceinline__ void row_stats_store(const double (&a)[7], int i, int ldx, const float* __restrict__ mm,
+                                                float* __restrict__ K_NA_spatial, float* __restrict__ K_NA_sigma2,
+                                                float* __restrict__ K_NA, float* __restrict__ PXB, double (&v)[4]) {
+  const double ksp = a[0] * (double)mm[i];
+  K_NA_spatial[i] = (float)ksp;
+  K_NA_sigma2[i] = (float)a[1];
+  K_NA[i] = (float)a[3];
+  PXB[i] = (float)a[4];
+  PXB[ldx + i] = (float)a[5];
+  PXB[2 * ldx + i] = (float)a[6];
+  v[0] = ksp; v[1] = a[1]; v[2] = a[3]; v[3] = a[2];
+}
+
+__global__ void __launch_bounds__(256)
+row_finalize_kernel(const float* __restrict__ rowpart, int nseg, int ldx, int NA, const float* __restrict__ mm,
+                    float* __restrict__ K_NA_spatial, float* __restrict__ K_NA_sigma2, float* __restrict__ K_NA,
+                    float* __restrict__ PXB, spb_scalars* sc, double* __restrict__ red_scratch, unsigned int* red_counter) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double v[4] = {0, 0, 0, 0};  // Sp_spatial, Sp_sigma2, Sp, S2
   if (i < NA) {
@@ -454,16 +467,80 @@ __global__ void row_finalize_kernel(const float* __restrict__ rowpart, int nseg,
 #pragma unroll
       for (int q = 0; q < 7; ++q) a[q] += (double)rowpart[((int64_t)s * 8 + q) * ldx + i];
     }
-    const double ksp = a[0] * (double)mm[i];
-    K_NA_spatial[i] = (float)ksp;
-    K_NA_sigma2[i] = (float)a[1];
-    K_NA[i] = (float)a[3];
-    PXB[i] = (float)a[4];
-    PXB[ldx + i] = (float)a[5];
-    PXB[2 * ldx + i] = (float)a[6];
-    v[0] = ksp; v[1] = a[1]; v[2] = a[3]; v[3] = a[2];
+    row_stats_store(a, i, ldx, mm, K_NA_spatial, K_NA_sigma2, K_NA, PXB, v);
   }
-  block_reduce_atomic<4>(v, sc->sums);
+  grid_reduce_ordered<4>(v, red_scratch, red_counter, sc->sums, false);
+}
+
+// ---- column-sharded pair ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+row_fold_kernel(const float* __restrict__ rowpart, int nseg, int ldx, int NA, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NA) return;
+  double a[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < nseg; ++s) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) a[q] += (double)rowpart[((int64_t)s * 8 + q) * ldx + i];
+  }
+#pragma unroll
+  for (int q = 0; q < 7; ++q) out[(int64_t)q * ldx + i] = a[q];
+}
+
+__global__ void __launch_bounds__(256)
+row_stats_finalize_kernel(const double* __restrict__ stat, int ldx, int NA, const float* __restrict__ mm,
+                          float* __restrict__ K_NA_spatial, float* __restrict__ K_NA_sigma2, float* __restrict__ K_NA,
+                          float* __restrict__ PXB, spb_scalars* sc, double* __restrict__ red_scratch,
+                          unsigned int* red_counter) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[4] = {0, 0, 0, 0};
+  if (i < NA) {
+    double a[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) a[q] = stat[(int64_t)q * ldx + i];
+    row_stats_store(a, i, ldx, mm, K_NA_spatial, K_NA_sigma2, K_NA, PXB, v);
+  }
+  grid_reduce_ordered<4>(v, red_scratch, red_counter, sc->sums, false);
+}
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Row statistics of the whole pair from every rank's partial sums, read straight from the peers' memory over NVLink:
+// block 0 announces "my partials of this epoch are complete" in every peer's flag array (system-scope release; the fold
+// kernel that produced them has finished), every block waits until all peers have announced the epoch, then each row sums
+// the W partial vectors IN RANK ORDER (so all ranks obtain the same bits) and finishes as row_finalize does.
+__global__ void __launch_bounds__(256)
+row_stats_p2p_kernel(const uint64_t* __restrict__ peer_stat, int parity, int rank, int world, uint64_t* flags,
+                     const uint64_t* __restrict__ peer_flags, uint64_t epoch, int ldx, int NA, const float* __restrict__ mm,
+                     float* __restrict__ K_NA_spatial, float* __restrict__ K_NA_sigma2, float* __restrict__ K_NA,
+                     float* __restrict__ PXB, spb_scalars* sc, double* __restrict__ red_scratch, unsigned int* red_counter) {
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint64_t*>(peer_flags[threadIdx.x]) + rank, epoch);
+  }
+  if (threadIdx.x < world) {
+    while (ld_acquire_sys(flags + threadIdx.x) < epoch) {
+    }
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[4] = {0, 0, 0, 0};
+  if (i < NA) {
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < world; ++r) {
+      const double* src = reinterpret_cast<const double*>(peer_stat[r]) + (int64_t)parity * 8 * ldx;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) a[q] += src[(int64_t)q * ldx + i];
+    }
+    row_stats_store(a, i, ldx, mm, K_NA_spatial, K_NA_sigma2, K_NA, PXB, v);
+  }
+  grid_reduce_ordered<4>(v, red_scratch, red_counter, sc->sums, false);
 }
 
 // bounding box of the current positions of each row block (valid rows only)
@@ -1128,8 +1205,38 @@ extern "C" int spb_posterior_argmax(const spb_em_params* p, int32_t iter, uint64
 
 
 extern "C" int spb_row_finalize(const spb_em_params* p, void* stream) {
+  if ((int64_t)((p->NA + 255) / 256) * 4 > p->red_scratch_doubles) return SPB_EINVAL;
   row_finalize_kernel<<<(p->NA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-      p->rowpart, p->seg2, p->ldx, p->NA, p->mm, p->K_NA_spatial, p->K_NA_sigma2, p->K_NA, p->PXB, p->sc);
+      p->rowpart, p->seg2, p->ldx, p->NA, p->mm, p->K_NA_spatial, p->K_NA_sigma2, p->K_NA, p->PXB, p->sc, p->red_scratch,
+      p->red_counter);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_row_fold(const spb_em_params* p, int32_t parity, void* stream) {
+  if (p->rowstat == nullptr) return SPB_EINVAL;
+  row_fold_kernel<<<(p->NA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p->rowpart, p->seg2, p->ldx, p->NA,
+                                                                          p->rowstat + (int64_t)(parity & 1) * 8 * p->ldx);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_row_stats_finalize(const spb_em_params* p, int32_t parity, void* stream) {
+  if (p->rowstat == nullptr || (int64_t)((p->NA + 255) / 256) * 4 > p->red_scratch_doubles) return SPB_EINVAL;
+  row_stats_finalize_kernel<<<(p->NA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      p->rowstat + (int64_t)(parity & 1) * 8 * p->ldx, p->ldx, p->NA, p->mm, p->K_NA_spatial, p->K_NA_sigma2, p->K_NA, p->PXB,
+      p->sc, p->red_scratch, p->red_counter);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_row_stats_p2p(const spb_em_params* p, int32_t parity, uint64_t epoch, void* stream) {
+  if (p->peer_rowstat == nullptr || p->peer_flags == nullptr || p->shard_flags == nullptr || p->shard_world < 1 ||
+      p->shard_world > 32 || (int64_t)((p->NA + 255) / 256) * 4 > p->red_scratch_doubles)
+    return SPB_EINVAL;
+  row_stats_p2p_kernel<<<(p->NA + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      p->peer_rowstat, parity & 1, p->shard_rank, p->shard_world, p->shard_flags, p->peer_flags, epoch, p->ldx, p->NA, p->mm,
+      p->K_NA_spatial, p->K_NA_sigma2, p->K_NA, p->PXB, p->sc, p->red_scratch, p->red_counter);
   SPB_CHECK_LAUNCH();
   return 0;
 }

@@ -286,7 +286,7 @@ gram_prepare_kernel(const float* __restrict__ UT, int64_t ldn, int64_t N, int K,
         if (n + 3 >= N) v.w = 0.f;
       }
     } else {
-      tot += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      tot += 0.0;
     }
     float4 h;
     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -296,10 +296,29 @@ gram_prepare_kernel(const float* __restrict__ UT, int64_t ldn, int64_t N, int K,
     *reinterpret_cast<float4*>(hi + n) = h;
     *reinterpret_cast<float4*>(lo + n) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   }
-  if (row >= K) {
-    double v1[1] = {tot};
-    block_reduce_atomic<1>(v1, sums + (row < K + E ? 1 + (row - K) : 0));
+  (void)tot;
+  (void)sums;
+}
+
+// sum_n w (sums[0]) and sum_n X_e (sums[1 + e]): one block per row, fixed summation order (reproducible)
+__global__ void __launch_bounds__(1024)
+gram_sums_kernel(int64_t N, int E, const float* __restrict__ w, const float* __restrict__ X, int64_t ldxx,
+                 double* __restrict__ sums) {
+  __shared__ double red[32];
+  const int row = blockIdx.x;  // 0 = w, 1 + e = X_e
+  const float* src = row == 0 ? w : X + (int64_t)(row - 1) * ldxx;
+  double t = 0.0;
+  for (int64_t n = threadIdx.x; n < N; n += 1024) t += (double)src[n];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double x = red[threadIdx.x];
+    x = warp_sum(x);
+    if (threadIdx.x == 0) sums[row] = x;
   }
+  if (row == 0 && threadIdx.x == 0)
+    for (int e = E; e < 3; ++e) sums[1 + e] = 0.0;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -391,14 +410,26 @@ extern "C" int spb_gram_prepare(const float* UT, int64_t ldn, int64_t N, int32_t
                                 const float* X, int64_t ldxx, int32_t E, float* B_hi, float* B_lo, double* sums4,
                                 void* stream) {
   if (ldn % 4 != 0 || (E > 0 && ldxx % 4 != 0) || K < 1 || E < 0 || E > 3) return SPB_EINVAL;
-  cudaError_t e = cudaMemsetAsync(sums4, 0, sizeof(double) * 4, ST);
-  if (e != cudaSuccess) return (int)e;
+  gram_sums_kernel<<<1 + E, 1024, 0, ST>>>(N, E, w, X, ldxx, sums4);
+  SPB_CHECK_LAUNCH();
   int gx = (int)((N / 4 + 255) / 256);
   if (gx > 592) gx = 592;
   if (gx < 1) gx = 1;
   if ((int64_t)gx * (K + E + 1) > 148 * 64) gx = (148 * 64) / (K + E + 1) + 1;  // enough CTAs, short rows need no more
   gram_prepare_kernel<<<dim3(gx, K + E + 1), 256, 0, ST>>>(UT, ldn, N, K, E, mean, w, X, ldxx, B_hi, B_lo, sums4);
   SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+// per-device shared-memory opt-in of the contraction kernel (idempotent; also called by spb_nonrigid_warm)
+int spb_gram_tc_warm() {
+  static bool attr_set[SPB_MAX_DEVICES] = {};
+  const int dev_ = spb_current_device();
+  if (!attr_set[dev_]) {
+    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem) + 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev_] = true;
+  }
   return 0;
 }
 
@@ -415,13 +446,7 @@ extern "C" int spb_gram_tc(const float* A_hi, const float* A_lo, const float* B_
   if ((rc = g_make_map(&ma_lo, A_lo, K, N, ldn))) return rc;
   if ((rc = g_make_map(&mb_hi, B_hi, K + E + 1, N, ldn))) return rc;
   if ((rc = g_make_map(&mb_lo, B_lo, K + E + 1, N, ldn))) return rc;
-  static bool attr_set[SPB_MAX_DEVICES] = {};
-  const int dev_ = spb_current_device();
-  if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(GramSmem) + 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set[dev_] = true;
-  }
+  if ((rc = spb_gram_tc_warm())) return rc;
   gram_tc_kernel<<<plan.ntiles * plan.nslices, kGThreads, sizeof(GramSmem) + 1024, ST>>>(ma_hi, ma_lo, mb_hi, mb_lo, plan, scratch);
   SPB_CHECK_LAUNCH();
   gram_reduce_kernel<<<dim3((K + E + 127) / 128, K), 128, 0, ST>>>(plan, scratch, mean, sums4, UtWU, UtX, 3);

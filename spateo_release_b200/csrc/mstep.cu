@@ -48,7 +48,7 @@ __global__ void scalar_update_kernel(spb_em_params p) {
   }
   sc->SpK = nS;
   sc->sigma2_related = S2 / ((double)p.D * sc->Sp_sigma2);
-  double g = exp(digamma_pos(p.gamma_a + sc->Sp_spatial) - digamma_pos(p.gamma_a + p.gamma_b + (double)p.NBb));
+  double g = exp(digamma_pos(p.gamma_a + sc->Sp_spatial) - digamma_pos(p.gamma_a + p.gamma_b + (double)(p.NB_total > 0 ? p.NB_total : p.NBb)));
   sc->gamma = fmax(fmin(g, 0.99), 0.01);
 }
 
@@ -164,10 +164,12 @@ weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, co
 constexpr int kSmallK = 32;
 __global__ void __launch_bounds__(256)
 gram_small_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const float* __restrict__ w,
-                  const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX, int rows_per_block) {
+                  const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX, int rows_per_block,
+                  double* __restrict__ partials, unsigned int* counter) {
   constexpr int kChunk = 128, kPitch = kChunk + 1;
   __shared__ float As[kSmallK][kPitch];
   __shared__ float Bs[kSmallK + 3][kPitch];
+  __shared__ bool is_last;
   const int KB = K + 3, nent = K * KB;
   constexpr int kPer = (kSmallK * (kSmallK + 3) + 255) / 256;  // 5 entries per thread at most
   double acc[kPer];
@@ -209,12 +211,34 @@ gram_small_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const
       acc[q] += s;
     }
   }
+  // deterministic fold over the CTAs: partials[block][entry], the last CTA to arrive adds them in block order
+#pragma unroll
+  for (int q = 0; q < kPer; ++q)
+    if (ek[q] >= 0) partials[(size_t)blockIdx.x * nent + threadIdx.x + q * 256] = acc[q];
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
 #pragma unroll
   for (int q = 0; q < kPer; ++q) {
     if (ek[q] < 0) continue;
-    if (el[q] < K) atomicAdd(&UtWU[(int64_t)ek[q] * K + el[q]], acc[q]);
-    else atomicAdd(&UtX[ek[q] * 3 + (el[q] - K)], acc[q]);
+    const int e = threadIdx.x + q * 256;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    unsigned b = 0;
+    for (; b + 4 <= gridDim.x; b += 4) {
+      s0 += partials[(size_t)(b + 0) * nent + e];
+      s1 += partials[(size_t)(b + 1) * nent + e];
+      s2 += partials[(size_t)(b + 2) * nent + e];
+      s3 += partials[(size_t)(b + 3) * nent + e];
+    }
+    for (; b < gridDim.x; ++b) s0 += partials[(size_t)b * nent + e];
+    const double t = (s0 + s1) + (s2 + s3);
+    if (el[q] < K) UtWU[(int64_t)ek[q] * K + el[q]] = t;
+    else UtX[ek[q] * 3 + (el[q] - K)] = t;
   }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 // SparseVFC E-step (dynamo scVectorField.SparseVFC get_P + bookkeeping; SURVEY.md Appendix E — parity unpinned):
@@ -522,7 +546,7 @@ __global__ void __launch_bounds__(256) rigid_moments_kernel(spb_em_params p) {
     m[27] += (double)p.K_NA_sigma2[i] * (double)p.SigmaDiag[i];
     m[28] += k;
   }
-  block_reduce_atomic<29>(m, p.moments);
+  grid_reduce_ordered<29>(m, p.red_scratch, p.red_counter + 1, p.moments, false);
 }
 
 // rotation / translation / sigma2 (morpho_class.py:1320-1402, 1426-1435) — one thread, fp64
@@ -748,8 +772,10 @@ extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
   if (p->K <= kSmallK) {
     int rows = (p->NA + 295) / 296;
     rows = ((rows + 127) / 128) * 128;
-    gram_small_kernel<<<(p->NA + rows - 1) / rows, 256, 0, ST>>>(p->UT, p->ldx, p->NA, p->K, p->K_NA, p->PXB_term, p->UtWU,
-                                                                 p->UtPXB, rows);
+    const int nblk = (p->NA + rows - 1) / rows;
+    if ((int64_t)nblk * p->K * (p->K + 3) > p->red_scratch_doubles) return SPB_EINVAL;
+    gram_small_kernel<<<nblk, 256, 0, ST>>>(p->UT, p->ldx, p->NA, p->K, p->K_NA, p->PXB_term, p->UtWU, p->UtPXB, rows,
+                                            p->red_scratch, p->red_counter + 2);
     SPB_CHECK_LAUNCH();
     return 0;
   }
@@ -771,7 +797,18 @@ extern "C" int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_
   if (K <= kSmallK) {
     int rows = (int)((N + 295) / 296);
     rows = ((rows + 127) / 128) * 128;
-    gram_small_kernel<<<(unsigned)((N + rows - 1) / rows), 256, 0, ST>>>(UT, ldx, (int)N, K, w, X3, UtWU, UtX, rows);
+    // stand-alone call (no spb_em_params): the block partials live in a small per-device buffer owned by the library
+    static double* scratch[SPB_MAX_DEVICES] = {};
+    static unsigned int* ticket[SPB_MAX_DEVICES] = {};
+    const int dev_ = spb_current_device();
+    const int nblk = (int)((N + rows - 1) / rows);
+    if (scratch[dev_] == nullptr) {
+      if (cudaMalloc(&scratch[dev_], sizeof(double) * 320 * kSmallK * (kSmallK + 3)) != cudaSuccess) return SPB_EUNSUPPORTED;
+      if (cudaMalloc(&ticket[dev_], sizeof(unsigned int)) != cudaSuccess) return SPB_EUNSUPPORTED;
+      cudaMemset(ticket[dev_], 0, sizeof(unsigned int));
+    }
+    if (nblk > 320) return SPB_EUNSUPPORTED;
+    gram_small_kernel<<<nblk, 256, 0, ST>>>(UT, ldx, (int)N, K, w, X3, UtWU, UtX, rows, scratch[dev_], ticket[dev_]);
     SPB_CHECK_LAUNCH();
     return 0;
   }
@@ -803,10 +840,7 @@ extern "C" int spb_nonrigid_blend(const spb_em_params* p, void* stream) {
   return 0;
 }
 
-extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
-  if (p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
-  const int Kp = (p->K + 1) & ~1;
-  const size_t smem = sizeof(double) * (3 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;  // A, V, warm-start scratch, rotations, pairing
+static int ensure_nonrigid_solve_attr() {
   static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
@@ -814,6 +848,22 @@ extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
+  return 0;
+}
+
+// One-time per-device kernel attributes of the non-rigid phase, so that the phase can be captured in a CUDA graph before
+// any of its kernels has been launched eagerly.
+extern "C" int spb_nonrigid_warm(void) {
+  const int rc = ensure_nonrigid_solve_attr();
+  return rc ? rc : spb_gram_tc_warm();
+}
+
+extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
+  if (p->K > SPB_MAX_K_FUSED) return SPB_EUNSUPPORTED;
+  const int Kp = (p->K + 1) & ~1;
+  const size_t smem = sizeof(double) * (3 * Kp * Kp + 2 * Kp) + sizeof(int) * Kp;  // A, V, warm-start scratch, rotations, pairing
+  int rc = ensure_nonrigid_solve_attr();
+  if (rc) return rc;
   // small matrices are latency-bound on the block barriers of the rotation rounds: fewer threads, cheaper barriers
   const int threads = Kp <= 16 ? 32 : (Kp <= 32 ? 64 : 256);
   nonrigid_solve_kernel<<<1, threads, smem, ST>>>(*p);
@@ -830,6 +880,7 @@ extern "C" int spb_field_apply(const spb_em_params* p, void* stream) {
 extern "C" int spb_rigid_moments(const spb_em_params* p, void* stream) {
   int blocks = (p->NA + 255) / 256;
   if (blocks > 592) blocks = 592;
+  if ((int64_t)blocks * 29 > p->red_scratch_doubles) return SPB_EINVAL;
   rigid_moments_kernel<<<blocks, 256, 0, ST>>>(*p);
   SPB_CHECK_LAUNCH();
   return 0;
