@@ -271,27 +271,37 @@ def run_vfc(args):
     n, M, D = args.vfc_cells, args.vfc_M, 3
     X, V, ctrl = vfc_problem(n, M)
     beta = 1.0 / 20.0**2
-    times, tms = [], []
     sampler = ClockSampler(0)
     from spateo_release_b200 import _capi
 
     lib = _capi.load_library()
-    launches0 = 0
-    for s in range(args.warmup + args.steps):
-        if s == args.warmup:
-            sampler.start()
-            launches0 = lib.spb_launch_count()
-        tm = {}
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        out = SparseVFC(X, V, Grid=None, M=M, beta=beta, lambda_=0.02, MaxIter=args.vfc_iters, ecr=0.0, ctrl_idx=ctrl,
-                        device="0", timings=tm)
-        torch.cuda.synchronize()
-        if s >= args.warmup:
-            times.append(time.perf_counter() - t0)
-            tms.append(tm)
+
+    def arm(gram, n_warm, n_steps, clocks_on):
+        times, tms, out = [], [], None
+        launches0 = 0
+        for s in range(n_warm + n_steps):
+            if s == n_warm:
+                launches0 = lib.spb_launch_count()
+                if clocks_on:
+                    sampler.start()
+            tm = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = SparseVFC(X, V, Grid=None, M=M, beta=beta, lambda_=0.02, MaxIter=args.vfc_iters, ecr=0.0, ctrl_idx=ctrl,
+                            device="0", timings=tm, gram=gram)
+            torch.cuda.synchronize()
+            if s >= n_warm:
+                times.append(time.perf_counter() - t0)
+                tms.append(tm)
+        return dict(sec=float(np.mean(times)), tms=tms, out=out,
+                    launches=int((lib.spb_launch_count() - launches0) // max(n_steps, 1)))
+
+    # the product default (reference-accurate normal equations, fp64 products) is the headline; the opt-in tensor-core
+    # contraction is measured beside it together with its deviation from the default's fit
+    main = arm("fp64", args.warmup, args.steps, True)
     clocks = sampler.stop()
-    sec = float(np.mean(times))
+    tens = arm("tensor", 1, max(1, min(args.steps, 3)), False)
+    out, sec, tms = main["out"], main["sec"], tens["tms"]
     iters = int(out["iteration"]) + 1
     units = float(n) * M * iters
     peaks = {}
@@ -303,12 +313,15 @@ def run_vfc(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1650.0)))
     tc_ms = float(np.mean([t["gram_tc_ms"].mean() for t in tms])) if "gram_tc_ms" in tms[0] else None
     flop = 2.0 * n * M * (M + D)  # 2 N M^2 + 2 N M D per iteration (the symmetric half would be N M^2)
+    k_out = n // 10
+    dev_V = float(np.abs(tens["out"]["V"][k_out:] - out["V"][k_out:]).max() / np.abs(out["V"]).max())
+    per_it = lambda T, k: float(np.mean([t[k].mean() for t in T]))
     roofline = None
     if tc_ms is not None:
         ach = flop / (tc_ms * 1e-3) / 1e12
         roofline = {
-            "bound": "tensor", "kernel": "gram_tc_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": ach / peak_tf, "traffic": None,
+            "bound": "tensor", "kernel": "gram_tc_kernel (opt-in gram='tensor' arm)", "achieved": ach, "peak": peak_tf,
+            "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense bf16)" if peaks else "fallback 1650 TFLOP/s",
             "definition": "algorithmic FLOP of one launch (2 N M (M + D): U^T P U and U^T P Y of one EM iteration) / mean "
                           "CUDA-event duration of spb_gram_tc (tcgen05 GEMM + 1% fp64 fold) inside the timed calls",
@@ -316,9 +329,22 @@ def run_vfc(args):
                     "the ceiling of this formulation is peak / 6; the kernel re-reads its operands (A 128-row and B 256-row "
                     "panels per output tile, 8 B per element as hi/lo fp32), which makes it HBM-bound at this shape",
             "operand_bytes_per_launch": float((6 * 128 + 4 * 256 + 4 * 16) * 8.0 * n),
-            "per_iteration_ms": {k: float(np.mean([t[k].mean() for t in tms])) for k in
-                                 ("estep_ms", "gram_prepare_ms", "gram_tc_ms", "solve_ms")},
+            "per_iteration_ms": {k: per_it(tms, k) for k in ("estep_ms", "gram_prepare_ms", "gram_tc_ms", "solve_ms")},
         }
+    fp64_gram_ms = per_it(main["tms"], "gram_ms")
+    fp64_path = {
+        "per_iteration_ms": {k: per_it(main["tms"], k) for k in ("estep_ms", "gram_ms", "solve_ms")},
+        "gram_kernel": "weighted_gram_kernel (fp64 FMA, block upper triangle)",
+        "gram_fp64_TFLOPs": float(n) * M * (M + 32) * 2 / (fp64_gram_ms * 1e-3) / 1e12,
+        "fp64_peak_TFLOPs_nominal": 37.0, "eigh_fallbacks": int(main["tms"][-1].get("eigh_fallbacks", 0)),
+    }
+    tensor_arm = {
+        "value": float(n) * M * (int(tens["out"]["iteration"]) + 1) / tens["sec"], "ms_per_step": tens["sec"] * 1e3,
+        "iterations_run": int(tens["out"]["iteration"]) + 1, "sigma2": tens["out"]["sigma2"],
+        "inlier_field_deviation_vs_default": dev_V,
+        "note": "opt-in approximate arm: fp32-level normal equations + ridge above the noise floor (a smoother fit, not the "
+                "reference solution); the deviation is max |V_tensor - V_default| over the inlier cells / max |V|",
+    }
     cpu = None
     if not args.no_cpu_baseline:
         from oracle.morpho_oracle import sparse_vfc
@@ -342,7 +368,7 @@ def run_vfc(args):
     print(json.dumps({
         "metric": "cell x control-point pairs/sec through SparseVFC EM", "value": units / sec, "unit": "pairs/s",
         "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 kernel matrix, 3xTF32 contraction, f64 fold / solve / posterior",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 kernel matrix, f64 normal equations / solve / posterior",
         "data": "synthetic",
         "config": {"workload": f"SparseVFC: {n} 3-D cells, {M} control points, {iters} EM iterations (ecr=0), lambda=0.02, host "
                                "arrays in/out; parity unpinned vs dynamo (third-party, absent)",
@@ -350,9 +376,9 @@ def run_vfc(args):
         "clocks": clocks,
         "e2e": {"value": units / sec, "unit": "pairs/s", "h2d_bytes_per_step": int(n * D * 8 * 2),
                 "d2h_bytes_per_step": int(n * (D + 1) * 8)},
-        "gpu_launches": int((lib.spb_launch_count() - launches0) // max(args.steps, 1)),
-        "roofline": roofline, "cpu_baseline": cpu,
-        "iterations_run": iters, "sigma2": out["sigma2"], "eigh_fallbacks": int(tms[-1].get("eigh_fallbacks", 0)),
+        "gpu_launches": main["launches"],
+        "roofline": roofline, "cpu_baseline": cpu, "fp64_path": fp64_path, "tensor_arm": tensor_arm,
+        "iterations_run": iters, "sigma2": out["sigma2"],
     }), flush=True)
 
 

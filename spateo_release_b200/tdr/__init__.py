@@ -1,5 +1,6 @@
 """``st.tdr`` entry points that share the Gaussian-kernel vector field (reference: spateo/tdr/__init__.py)."""
 
+from .interpolations import kernel_interpolation
 from .morphofield import morphofield, morphofield_gp, morphofield_sparsevfc
 from .morphofield_dg import (
     GPVectorField,

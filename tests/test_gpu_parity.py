@@ -233,7 +233,7 @@ def test_sparse_mode_edge_cases():
 
 @pytest.mark.parametrize("case", ["2d_full", "3d_full_warp", "2d_full_nonn_euc", "3d_svi", "2d_full_guide_both",
                                   "2d_svi_guide_nonrigid", "2d_full_sparse48", "3d_svi_sparse32", "c1_2d_svi",
-                                  "c1_2d_full_warp", "2d_full_geodist"])
+                                  "c1_2d_full_warp"])
 def test_full_run_matches_reference(golden, case):
     """Whole alignment through the public class: aligned coordinates within 1e-3 (relative to the coordinate range)
     of BOTH the float32 and the float64 reference runs; sigma2 / gamma close; P against the float64 reference."""
@@ -273,6 +273,28 @@ def test_full_run_matches_reference(golden, case):
               "sigma2_variance", "method", "norm_dict", "kernel_type"):
         assert k in m.vecfld
     assert m.vecfld["t"].shape == (1, m.D) and m.vecfld["Coff"].shape == (m.K, m.D)
+
+
+def test_geodesic_kernel_matches_reference(golden):
+    """kernel_type="geodist" (morpho_class.py:865-871, utils.py:1161-1217): the inducing kernel built from shortest paths on
+    the kNN graph equals the reference's networkx construction, and the run tracks the reference's sigma2 / gamma trajectory
+    through the rigid phase and the first non-rigid iterations. (Upstream marks this path TODO and it is unstable there: in
+    the reference run of this fixture the deformation coefficients grow to 85 at iteration 95 and 1085 at iteration 110 in
+    normalised units, gamma collapses, and its own float32 and float64 runs end 0.65 coordinate ranges apart — so nothing
+    after the first non-rigid iterations is comparable.)"""
+    g = golden("2d_full_geodist")
+    m = _model(g)
+    assert np.abs(m.U - g["pre_U"]).max() < 2e-6
+    assert np.abs(m.GammaSparse - g["pre_GammaSparse"]).max() < 2e-6
+    assert np.array_equal(m.inducing_variables.astype(np.float32), g["pre_inducing_variables"].astype(np.float32))
+    m.run()
+    n = m.trace.shape[0]
+    assert np.isfinite(m.XAHat).all() and np.isfinite(m.optimal_RnA).all()
+    print("\n[geodist] gamma ours", np.round(m.trace[78:100:3, 1], 4), "\n[geodist] gamma ref ", np.round(g["traj_gamma"][78:100:3], 4))
+    upto = 87  # nonrigid_start_iter = 80: six non-rigid iterations
+    assert np.abs(m.trace[:upto, 0] - g["traj_sigma2"][:upto]).max() < 2e-2 * g["traj_sigma2"].max()
+    assert np.abs(m.trace[:upto, 1] - g["traj_gamma"][:upto]).max() < 2e-2
+    assert m.vecfld["kernel_type"] == "geodist"
 
 
 def test_trajectory_tracks_reference(golden):
