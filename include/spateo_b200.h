@@ -106,6 +106,7 @@ typedef struct spb_em_params {
   double inl_Sa[3];            /* inlier_P^T inlier_A */
   double inl_Sb[3];            /* inlier_P^T inlier_B */
   double inl_Mab[9];           /* sum_n P_n a_n b_n^T */
+  double pinv_eps;             /* machine epsilon of the reference's SigmaInv dtype: pinv cutoff = K * pinv_eps * max|ev| (scipy.linalg.pinv, utils.py:1435) */
   double g_weight;             /* guidance_weight */
   double g_meanXB;             /* X_BI.mean() over ALL elements (the reference adds this scalar to every axis) */
   double g_meanXA;             /* X_AI.mean() */
@@ -259,6 +260,9 @@ int spb_nonrigid_accumulate(const spb_em_params* p, void* stream);           /* 
 int spb_nonrigid_solve(const spb_em_params* p, void* stream);                /* morpho_class.py:1273-1291 (K<=64) */
 int spb_nonrigid_blend(const spb_em_params* p, void* stream);                /* SigmaInv assembly only (K>64 path) */
 int spb_field_apply(const spb_em_params* p, void* stream);                   /* morpho_class.py:1293-1298 */
+/* the same from a factor of Sigma: Sigma = G G^T, G [K][ldg] with only the first *rank (device int32) columns non-zero; K * rank
+   work per moving cell instead of K^2 (large inducing sets, where the eigen-solve runs outside spb_nonrigid_solve) */
+int spb_field_apply_lowrank(const spb_em_params* p, const double* G, int32_t ldg, const int32_t* rank, void* stream); /* morpho_class.py:1293-1298 */
 int spb_rigid_moments(const spb_em_params* p, void* stream);                 /* morpho_class.py:1312-1318,1356-1357,1427 */
 int spb_rigid_solve(const spb_em_params* p, int32_t iter, void* stream);     /* morpho_class.py:1320-1402,1426-1435 */
 int spb_row_update(const spb_em_params* p, void* stream);                    /* morpho_class.py:1404,293,1087 */

@@ -141,6 +141,7 @@ def load_library():
         "spb_nonrigid_solve": ([EP, P], C.c_int),
         "spb_nonrigid_blend": ([EP, P], C.c_int),
         "spb_field_apply": ([EP, P], C.c_int),
+        "spb_field_apply_lowrank": ([EP, P, I32, P, P], C.c_int),
         "spb_rigid_moments": ([EP, P], C.c_int),
         "spb_rigid_solve": ([EP, I32, P], C.c_int),
         "spb_row_update": ([EP, P], C.c_int),

@@ -1007,6 +1007,7 @@ class Morpho_pairwise:
         p.sparse_k = int(self.sparse_top_k) if self.sparse_calculation_mode else 0
         p.lambdaVF, p.gamma_a, p.gamma_b = float(self.lambdaVF), float(self.gamma_a), float(self.gamma_b)
         p.samples_s = float(self.samples_s)
+        p.pinv_eps = self._pinv_eps()
         p.nn_init_weight = float(self.nn_init_weight)
         p.sigma2_variance_decress = float(self.sigma2_variance_decress)
         p.sigma2_variance_end = float(self.sigma2_variance_end)
@@ -1138,6 +1139,12 @@ class Morpho_pairwise:
                 dist.all_reduce(view)
             check(lib.spb_row_stats_finalize(C.byref(p), parity, st), "spb_row_stats_finalize")
 
+    def _pinv_eps(self) -> float:
+        """Machine epsilon behind scipy.linalg.pinv's default cutoff in the reference (utils.py:1435): float32 for the
+        Euclidean kernel; the geodesic kernel matrix is float64 there (con_K_graph, utils.py:1208-1217), which promotes
+        SigmaInv and makes the cutoff K * eps(float64)."""
+        return 2.220446049250313e-16 if self.kernel_type == "geodist" else 1.1920928955078125e-07
+
     def _read_scalars(self) -> SpbScalars:
         raw = self._state["sc"].cpu().numpy().tobytes()
         return SpbScalars.from_buffer_copy(raw)
@@ -1146,25 +1153,34 @@ class Morpho_pairwise:
     # the EM loop
     # ------------------------------------------------------------------------------------------------------------------
     def _nonrigid_solve_large_K(self, st):
-        """K > SPB_MAX_K_FUSED: eigen pseudo-inverse through cuSOLVER (torch.linalg.eigh, fp64), same cutoff rule."""
+        """K > SPB_MAX_K_FUSED: eigen pseudo-inverse through cuSOLVER (torch.linalg.eigh, fp64), same cutoff rule as
+        scipy.linalg.pinv on the reference's fp32 matrix (utils.py:1435). Everything stays on the device: the kept
+        eigen-directions are sorted first and handed to the row kernel as a factor of Sigma, with their count in device memory."""
         lib, p, s = self._lib, self._params, self._state
         check(lib.spb_nonrigid_blend(C.byref(p), st), "spb_nonrigid_blend")
         A = s["SigmaInv"]
         A = 0.5 * (A + A.T)
         ev, V = torch.linalg.eigh(A)
-        cutoff = ev.abs().max() * self.K * 1.1920928955078125e-07
-        inv = torch.where(ev.abs() > cutoff, 1.0 / ev, torch.zeros_like(ev))
-        Sigma = (V * inv) @ V.T
-        s["Sigma"].copy_(Sigma)
+        ev, V = ev.flip(0), V.flip(1)  # descending: directions above the cutoff come first
+        cutoff = ev.abs().max() * self.K * self._pinv_eps()
+        keep = ev.abs() > cutoff
+        inv = torch.where(keep, 1.0 / ev, torch.zeros_like(ev))
+        VS = V * inv
+        s["Sigma"].copy_(VS @ V.T)
         rhs = s["UtPXB"]
         g_nonrigid = self.guidance and self.guidance_effect in ("nonrigid", "both")
         if g_nonrigid:  # morpho_class.py:1286-1288, 1294-1295 (the SigmaInv part is added by spb_nonrigid_blend)
-            sc = self._read_scalars()
-            cg = sc.sigma2 * float(self.guidance_weight) * sc.Sp / self.X_AI.shape[0]
+            sc = s["sc"][:80].view(torch.float64)  # sigma2 = [0], Sp = [3] (spb_scalars layout)
+            cg = sc[0] * float(self.guidance_weight) * sc[3] / self.X_AI.shape[0]
             rhs = rhs + cg * (s["g_UI"].T @ (s["g_XB"] - s["g_RA"]))
-        s["Coff"].copy_(Sigma @ rhs)
+        s["Coff"].copy_(VS @ (V.T @ rhs))
         if g_nonrigid:
             s["g_VA"].copy_(s["g_UI"] @ s["Coff"])
+        # factor of Sigma for the row kernel: G = V sqrt(|inv|) sign-safe (kept eigenvalues of the PSD matrix are positive)
+        G = s.setdefault("sigma_factor", torch.zeros((self.K, self.K), dtype=torch.float64, device=self._dev))
+        G.copy_(V * torch.sqrt(inv.clamp_min(0.0)))
+        rank = s.setdefault("sigma_rank", torch.zeros((1,), dtype=torch.int32, device=self._dev))
+        rank.copy_((keep & (ev > 0)).sum().to(torch.int32).reshape(1))
 
     def _iteration(self, it: int, st, capture_P: bool = False, sweep_events: Optional[list] = None):
         """One EM iteration (morpho_class.py:280-294). The fused C entry point is used unless the iteration has to be
@@ -1184,9 +1200,11 @@ class Morpho_pairwise:
             check(lib.spb_nonrigid_accumulate(C.byref(p), st), "spb_nonrigid_accumulate")
             if large_K:
                 self._nonrigid_solve_large_K(st)
+                check(lib.spb_field_apply_lowrank(C.byref(p), ptr(self._state["sigma_factor"]), self.K,
+                                                  ptr(self._state["sigma_rank"]), st), "spb_field_apply_lowrank")
             else:
                 check(lib.spb_nonrigid_solve(C.byref(p), st), "spb_nonrigid_solve")
-            check(lib.spb_field_apply(C.byref(p), st), "spb_field_apply")
+                check(lib.spb_field_apply(C.byref(p), st), "spb_field_apply")
         check(lib.spb_rigid_moments(C.byref(p), st), "spb_rigid_moments")
         check(lib.spb_rigid_solve(C.byref(p), it, st), "spb_rigid_solve")
         check(lib.spb_row_update(C.byref(p), st), "spb_row_update")

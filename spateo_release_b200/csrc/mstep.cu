@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
   if (tid == 0) {
     double mx = 0;
     for (int r = 0; r < K; ++r) mx = fmax(mx, fabs(A[r * Kp + r]));
-    s_diag = mx * (double)K * 1.1920928955078125e-07;
+    s_diag = mx * (double)K * p.pinv_eps;
   }
   __syncthreads();
   const double cutoff = s_diag;
@@ -509,6 +509,40 @@ __global__ void __launch_bounds__(128) field_apply_kernel(spb_em_params p) {
     double tk = 0;
     for (int l = 0; l < K; ++l) tk += p.Sigma[(int64_t)k * K + l] * (double)p.UT[(int64_t)l * p.ldx + i];
     quad += uk * tk;
+  }
+  p.VnA[i] = (float)v0;
+  p.VnA[p.ldx + i] = (float)v1;
+  p.VnA[2 * p.ldx + i] = (float)v2;
+  p.SigmaDiag[i] = (float)(s2 * quad);
+}
+
+// Same outputs from a FACTOR of Sigma: Sigma = G G^T with G = V_kept diag(1 / sqrt(ev_kept)) [K][ldg], only the first *rank
+// columns non-zero (eigenvalues above the pseudo-inverse cutoff, sorted first). diag(U Sigma U^T)_n = |G^T u_n|^2 costs
+// K * rank instead of K^2 per moving cell; the spectrum of SigmaInv decays fast, so rank << K for large inducing sets.
+__global__ void __launch_bounds__(128) field_apply_lowrank_kernel(spb_em_params p, const double* __restrict__ G, int ldg,
+                                                                  const int32_t* __restrict__ rank_ptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.NA) return;
+  const int K = p.K, r = min(*rank_ptr, K);
+  const double s2 = p.sc->sigma2;
+  double v0 = 0, v1 = 0, v2 = 0;
+  for (int k = 0; k < K; ++k) {
+    const double uk = (double)p.UT[(int64_t)k * p.ldx + i];
+    v0 += uk * p.Coff[k * 3 + 0];
+    v1 += uk * p.Coff[k * 3 + 1];
+    v2 += uk * p.Coff[k * 3 + 2];
+  }
+  double quad = 0.0;
+  for (int j0 = 0; j0 < r; j0 += 8) {
+    double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < K; ++k) {
+      const double uk = (double)p.UT[(int64_t)k * p.ldx + i];
+      const double* g = G + (int64_t)k * ldg + j0;  // columns beyond the rank are zero: the last chunk may overrun it
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) t[jj] += uk * ((j0 + jj < ldg) ? g[jj] : 0.0);
+    }
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) quad += t[jj] * t[jj];
   }
   p.VnA[i] = (float)v0;
   p.VnA[p.ldx + i] = (float)v1;
@@ -873,6 +907,13 @@ extern "C" int spb_nonrigid_solve(const spb_em_params* p, void* stream) {
 
 extern "C" int spb_field_apply(const spb_em_params* p, void* stream) {
   field_apply_kernel<<<(p->NA + 127) / 128, 128, 0, ST>>>(*p);
+  SPB_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int spb_field_apply_lowrank(const spb_em_params* p, const double* G, int32_t ldg, const int32_t* rank, void* stream) {
+  if (G == nullptr || rank == nullptr || ldg < 1) return SPB_EINVAL;
+  field_apply_lowrank_kernel<<<(p->NA + 127) / 128, 128, 0, ST>>>(*p, G, ldg, rank);
   SPB_CHECK_LAUNCH();
   return 0;
 }
