@@ -842,7 +842,8 @@ def main():
         m.__dict__.pop("_GT", None)
         m.__dict__.pop("_state", None)
         torch.cuda.empty_cache()
-        for tag, kw in (("svi_default_batch", dict(SVI_mode=True, K=args.K)), ("full_em_K200", dict(SVI_mode=False, K=200))):
+        for tag, kw in (("svi_default_batch", dict(SVI_mode=True, K=args.K)), ("full_em_K200", dict(SVI_mode=False, K=200)),
+                        ("full_em_K500", dict(SVI_mode=False, K=500))):
             np.random.seed(rank)
             m2 = st.align.Morpho_pairwise(sampleA=B, sampleB=A, max_iter=args.max_iter, nn_init=True, verbose=False,
                                           device=str(local_rank), materialize_P=False, **kw)

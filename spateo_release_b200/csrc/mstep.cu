@@ -80,26 +80,28 @@ __global__ void pxb_term_kernel(spb_em_params p) {
   }
 }
 
-// U^T diag(K_NA) U  and  U^T PXB_term : 32x32 output tiles, fp64 accumulation, atomics into the K x K accumulator.
+// U^T diag(K_NA) U  and  U^T PXB_term with fp64 products (the reference-accurate path of SparseVFC, and of the alignment when
+// SPB_GRAM=simt): 64 x 64 output tiles of the block upper triangle, 256 threads x (4 x 4) register tiles, operands converted to
+// double ONCE while they are staged through shared memory (32 rows of n per chunk), atomics into the K x K accumulator.
 // grid.x = row chunks, grid.y = (kt, lt) tile pairs with kt <= lt.
-constexpr int kAccRows = 128;
-// rows per CTA of weighted_gram_kernel: at least two CTAs per SM in flight even when K <= 32 gives a single tile pair
+constexpr int kGT = 64;        // tile edge
+constexpr int kGC = 32;        // rows of n per shared-memory chunk
+constexpr int kAccRows = 128;  // granularity of the row chunks
 inline int gram_rows_per_block(int64_t N, int npairs) {
   const int64_t want_chunks = (2 * 148 + npairs - 1) / npairs;
   int64_t rows = (N + want_chunks - 1) / want_chunks;
   rows = ((rows + kAccRows - 1) / kAccRows) * kAccRows;
   if (rows < 2 * kAccRows) rows = 2 * kAccRows;
-  if (rows > 2048) rows = 2048;
+  if (rows > 16384) rows = 16384;
   return (int)rows;
 }
 __global__ void __launch_bounds__(256)
 weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, const float* __restrict__ w,
                      const float* __restrict__ X3, double* __restrict__ UtWU, double* __restrict__ UtX,
                      int rows_per_block, int ntile) {
-  __shared__ float Uk[32][kAccRows + 1];
-  __shared__ float Ul[32][kAccRows + 1];
-  __shared__ float Xs[3][kAccRows];
-  // decode the tile pair
+  __shared__ double As[kGC][kGT + 1];
+  __shared__ double Bs[kGC][kGT + 1];
+  __shared__ double Xs[kGC][3];
   int kt = 0, lt = 0;
   {
     int q = blockIdx.y;
@@ -113,48 +115,59 @@ weighted_gram_kernel(const float* __restrict__ UT, int64_t ldx, int N, int K, co
     }
   }
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-  double acc[2][2] = {{0, 0}, {0, 0}};
-  double accx = 0.0;  // U^T X entry (threads < 96 of diagonal tiles)
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  double accx = 0.0;  // U^T X entry (threads < 192 of diagonal tiles: row kk = tid / 3, column d = tid % 3)
   const int r_begin = blockIdx.x * rows_per_block;
   const int r_end = min(N, r_begin + rows_per_block);
-  for (int r0 = r_begin; r0 < r_end; r0 += kAccRows) {
-    const int nr = min(kAccRows, r_end - r0);
+  for (int r0 = r_begin; r0 < r_end; r0 += kGC) {
+    const int nr = min(kGC, r_end - r0);
     __syncthreads();
-    for (int q = threadIdx.x; q < 32 * kAccRows; q += 256) {
-      const int kk = q / kAccRows, rr = q % kAccRows;
-      const int k = kt * 32 + kk, l = lt * 32 + kk;
+    for (int q = threadIdx.x; q < kGT * kGC; q += 256) {
+      const int kk = q / kGC, rr = q % kGC;  // a warp reads 32 consecutive n of one row: coalesced
+      const int k = kt * kGT + kk, l = lt * kGT + kk;
       const bool ok = rr < nr;
       const float wv = ok ? w[r0 + rr] : 0.f;
-      Uk[kk][rr] = (ok && k < K) ? UT[(int64_t)k * ldx + r0 + rr] : 0.f;
-      Ul[kk][rr] = (ok && l < K) ? UT[(int64_t)l * ldx + r0 + rr] * wv : 0.f;
+      As[rr][kk] = (ok && k < K) ? (double)UT[(int64_t)k * ldx + r0 + rr] : 0.0;
+      // w * u is rounded to fp32 first, like the reference's fp32 product (and the small-K kernel)
+      Bs[rr][kk] = (ok && l < K) ? (double)(UT[(int64_t)l * ldx + r0 + rr] * wv) : 0.0;
     }
-    if (kt == lt) {
-      for (int q = threadIdx.x; q < 3 * kAccRows; q += 256) {
-        const int d = q / kAccRows, rr = q % kAccRows;
-        Xs[d][rr] = rr < nr ? X3[(int64_t)d * ldx + r0 + rr] : 0.f;
-      }
+    if (kt == lt && threadIdx.x < kGC * 3) {
+      const int rr = threadIdx.x / 3, d = threadIdx.x % 3;
+      Xs[rr][d] = rr < nr ? (double)X3[(int64_t)d * ldx + r0 + rr] : 0.0;
     }
     __syncthreads();
-    for (int rr = 0; rr < kAccRows; ++rr) {
-      const double a0 = Uk[2 * ty][rr], a1 = Uk[2 * ty + 1][rr];
-      const double b0 = Ul[2 * tx][rr], b1 = Ul[2 * tx + 1][rr];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+#pragma unroll 8
+    for (int rr = 0; rr < kGC; ++rr) {
+      double a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a[q] = As[rr][ty * 4 + q];
+        b[q] = Bs[rr][tx * 4 + q];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
     }
-    if (kt == lt && threadIdx.x < 96) {
+    if (kt == lt && threadIdx.x < kGT * 3) {
       const int kk = threadIdx.x / 3, d = threadIdx.x % 3;
-      for (int rr = 0; rr < kAccRows; ++rr) accx += (double)Uk[kk][rr] * (double)Xs[d][rr];
+      for (int rr = 0; rr < kGC; ++rr) accx += As[rr][kk] * Xs[rr][d];
     }
   }
-  for (int a = 0; a < 2; ++a)
-    for (int b = 0; b < 2; ++b) {
-      const int k = kt * 32 + 2 * ty + a, l = lt * 32 + 2 * tx + b;
+  for (int a = 0; a < 4; ++a)
+    for (int b = 0; b < 4; ++b) {
+      const int k = kt * kGT + ty * 4 + a, l = lt * kGT + tx * 4 + b;
       if (k < K && l < K) {
         atomicAdd(&UtWU[(int64_t)k * K + l], acc[a][b]);
         if (kt != lt) atomicAdd(&UtWU[(int64_t)l * K + k], acc[a][b]);
       }
     }
-  if (kt == lt && threadIdx.x < 96) {
-    const int k = kt * 32 + threadIdx.x / 3, d = threadIdx.x % 3;
+  if (kt == lt && threadIdx.x < kGT * 3) {
+    const int k = kt * kGT + threadIdx.x / 3, d = threadIdx.x % 3;
     if (k < K) atomicAdd(&UtX[k * 3 + d], accx);
   }
 }
@@ -813,7 +826,7 @@ extern "C" int spb_nonrigid_accumulate(const spb_em_params* p, void* stream) {
     SPB_CHECK_LAUNCH();
     return 0;
   }
-  const int ntile = (p->K + 31) / 32;
+  const int ntile = (p->K + kGT - 1) / kGT;
   const int npairs = ntile * (ntile + 1) / 2;
   const int rows_per_block = gram_rows_per_block(p->NA, npairs);
   dim3 grid((p->NA + rows_per_block - 1) / rows_per_block, npairs);
@@ -846,7 +859,7 @@ extern "C" int spb_weighted_gram(const float* UT, int64_t ldx, int64_t N, int32_
     SPB_CHECK_LAUNCH();
     return 0;
   }
-  const int ntile = (K + 31) / 32;
+  const int ntile = (K + kGT - 1) / kGT;
   const int npairs = ntile * (ntile + 1) / 2;
   const int rows_per_block = gram_rows_per_block(N, npairs);
   dim3 grid((unsigned)((N + rows_per_block - 1) / rows_per_block), npairs);
