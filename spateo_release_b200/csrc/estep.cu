@@ -121,9 +121,17 @@ __device__ __forceinline__ float hsum(u64 v) {
   return a + b;
 }
 // squared distance of two moving cells (packed) to one fixed cell whose coordinates are pre-duplicated (y,y)
+// kDim = 2: slices without a third coordinate skip its term (fma(0, 0, r) = r exactly, so the result is bit-identical to the
+// 3-term form on zero-padded coordinates — col_select_kernel's scalar pair_weight relies on that)
+template <int kDim = 3>
 __device__ __forceinline__ u64 sqdist2(u64 x0, u64 x1, u64 x2, u64 y0, u64 y1, u64 y2) {
-  const u64 d0 = sub2(x0, y0), d1 = sub2(x1, y1), d2 = sub2(x2, y2);
-  return fma2(d2, d2, fma2(d1, d1, mul2(d0, d0)));
+  const u64 d0 = sub2(x0, y0), d1 = sub2(x1, y1);
+  u64 r = fma2(d1, d1, mul2(d0, d0));
+  if constexpr (kDim == 3) {
+    const u64 d2 = sub2(x2, y2);
+    r = fma2(d2, d2, r);
+  }
+  return r;
 }
 
 // Butterfly transpose-reduce: NV (= 32 or 16) per-lane values are summed across the 32 lanes of a warp in
@@ -175,7 +183,7 @@ __device__ __forceinline__ RowRegs load_rows(const float* __restrict__ XA, int64
 }
 
 // sweep 1, one pipeline stage: per column the four partial sums of this thread's 4 rows (index v * kColStage + jj)
-template <int kColStage, int kStages>
+template <int kColStage, int kStages, int kDim = 3>
 __device__ __forceinline__ void sweep1_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
                                              u64 CQ, u64 CS, float (&acc)[4 * kColStage]) {
 #pragma unroll
@@ -183,8 +191,8 @@ __device__ __forceinline__ void sweep1_stage(const SmemLayoutT<kColStage, kStage
     const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);  // (y0,y0) (y1,y1)
     const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (0,0)
     const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
-    const u64 da = sqdist2(R.xa0, R.xa1, R.xa2, ya.x, ya.y, yb.x);
-    const u64 db = sqdist2(R.xb0, R.xb1, R.xb2, ya.x, ya.y, yb.x);
+    const u64 da = sqdist2<kDim>(R.xa0, R.xa1, R.xa2, ya.x, ya.y, yb.x);
+    const u64 db = sqdist2<kDim>(R.xb0, R.xb1, R.xb2, ya.x, ya.y, yb.x);
     const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
     const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
     acc[0 * kColStage + jj] = hsum(add2(sa, sb));
@@ -226,7 +234,7 @@ __device__ __forceinline__ u64 keep_ge(u64 w, float tau) {
   return pk(a >= tau ? a : 0.f, b >= tau ? b : 0.f);
 }
 
-template <int kColStage, int kStages, bool kSparse>
+template <int kColStage, int kStages, bool kSparse, int kDim = 3>
 __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
                                              u64 CQ, u64 CS, S2Acc& A) {
 #pragma unroll
@@ -235,10 +243,9 @@ __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStage
     const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);  // (y2,y2) (a,a)
     const ulonglong2 c2 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][2]);  // (b,b)  (c,c)
     const ulonglong2 c3 = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][3]);  // (c y0, c y0) (c y1, c y1)
-    const u64 cy2 = *reinterpret_cast<const u64*>(&sm.cols[s][jj][4]);               // (c y2, c y2)
     const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
-    const u64 da = sqdist2(R.xa0, R.xa1, R.xa2, c0.x, c0.y, c1.x);
-    const u64 db = sqdist2(R.xb0, R.xb1, R.xb2, c0.x, c0.y, c1.x);
+    const u64 da = sqdist2<kDim>(R.xa0, R.xa1, R.xa2, c0.x, c0.y, c1.x);
+    const u64 db = sqdist2<kDim>(R.xb0, R.xb1, R.xb2, c0.x, c0.y, c1.x);
     const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
     const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
     A.spa = fma2(sa, c1.y, A.spa);
@@ -261,8 +268,11 @@ __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStage
     A.pxb = fma2(wb, c3.x, A.pxb);
     A.pya = fma2(wa, c3.y, A.pya);
     A.pyb = fma2(wb, c3.y, A.pyb);
-    A.pza = fma2(wa, cy2, A.pza);
-    A.pzb = fma2(wb, cy2, A.pzb);
+    if constexpr (kDim == 3) {
+      const u64 cy2 = *reinterpret_cast<const u64*>(&sm.cols[s][jj][4]);  // (c y2, c y2)
+      A.pza = fma2(wa, cy2, A.pza);
+      A.pzb = fma2(wb, cy2, A.pzb);
+    }
   }
 }
 
@@ -286,7 +296,7 @@ __device__ __forceinline__ float sqdist(float x0, float x1, float x2, const floa
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 1: column sums
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kColStage, int kStages, int kMinBlocks>
+template <int kColStage, int kStages, int kMinBlocks, int kDim = 3>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colgeom, const float* __restrict__ XA, const float* __restrict__ lm,
@@ -325,7 +335,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     const int pb = cr.begin + st * kColStage;
     constexpr int NV = 4 * kColStage;  // partial sums per thread per stage, index v * kColStage + jj
     float acc[NV];
-    sweep1_stage<kColStage, kStages>(sm, s, tid, R, CQ, CS, acc);
+    sweep1_stage<kColStage, kStages, kDim>(sm, s, tid, R, CQ, CS, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // stage buffer is free again
     butterfly_reduce<NV>(acc, lane);
@@ -393,7 +403,7 @@ col_finalize_kernel(const float* __restrict__ colpart, int nrb, int nbb_pad, int
 // ---------------------------------------------------------------------------------------------------------------------
 // sweep 2: row statistics
 // ---------------------------------------------------------------------------------------------------------------------
-template <int kColStage, int kStages, int kMinBlocks, bool kSparse, int kDbg = 0>
+template <int kColStage, int kStages, int kMinBlocks, bool kSparse, int kDbg = 0, int kDim = 3>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
@@ -432,7 +442,7 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     const int s = st % kStages;
     if (kDbg != 2 || st < kStages) mbar_wait(&sm.full[s], (st / kStages) & 1);
     if constexpr (kDbg == 1) stream_only_stage<kColStage, kStages>(sm, s, tid, A);
-    else sweep2_stage<kColStage, kStages, kSparse>(sm, s, tid, R, CQ, CS, A);
+    else sweep2_stage<kColStage, kStages, kSparse, kDim>(sm, s, tid, R, CQ, CS, A);
     if constexpr (kDbg != 2) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[s]);
@@ -1046,34 +1056,34 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
 int g_sweep_dbg = 0;  // 0 product, 1 stream-only sweep 2, 2 arithmetic-only sweep 2 (diagnostics, spb_set_sweep_config(16 * mode + cfg))
 int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
-template <int C, int S, int B>
+template <int C, int S, int B, int DIM = 3>
 int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
   static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
   dim3 grid(p->ldx / kRowTile, p->seg1);
-  estep_sweep1_kernel<C, S, B><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
+  estep_sweep1_kernel<C, S, B, DIM><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
                                                                   p->colpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
 
-template <int C, int S, int B, bool SP, int DBG = 0>
+template <int C, int S, int B, bool SP, int DBG = 0, int DIM = 3>
 int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
   using Smem = SmemLayoutT<C, S>;
   static bool attr_set[SPB_MAX_DEVICES] = {};  // the opt-in is per device (one process may drive several GPUs)
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
-    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP, DBG, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
   dim3 grid(p->ldx / kRowTile, p->seg2);
-  estep_sweep2_kernel<C, S, B, SP, DBG><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
+  estep_sweep2_kernel<C, S, B, SP, DBG, DIM><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
                                                                   p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
   return 0;
 }
@@ -1130,6 +1140,7 @@ extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stre
   // exactly those entries, every other entry is overwritten by this launch
   if (g_sweep_cfg == 1) rc = launch_sweep1<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep1<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (p->D == 2) rc = launch_sweep1<8, 3, 2, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep1<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   if (rc) return rc;
   SPB_CHECK_LAUNCH();
@@ -1145,11 +1156,13 @@ extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
 
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
-  if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  if (p->sparse_k > 0 && p->D == 2) rc = launch_sweep2<8, 3, 2, true, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_dbg == 1) rc = launch_sweep2<8, 3, 2, false, 1>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_dbg == 2) rc = launch_sweep2<8, 3, 2, false, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (p->D == 2) rc = launch_sweep2<8, 3, 2, false, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   else rc = launch_sweep2<8, 3, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   if (rc) return rc;
   SPB_CHECK_LAUNCH();
