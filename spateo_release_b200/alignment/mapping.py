@@ -23,7 +23,13 @@ class ArgmaxPi:
     """Row and column maxima of a posterior that was never materialised (shape ``(n_rows, n_cols)``).
 
     ``row_arg[i]`` / ``row_val[i]``: lowest column index and value of the maximum of row i; ``col_arg`` / ``col_val``
-    likewise per column. ``.T`` swaps the roles (the drivers hand ``P.T`` to the mapping helpers)."""
+    likewise per column. ``.T`` swaps the roles (the drivers hand ``P.T`` to the mapping helpers).
+
+    Tie-breaking differs from the reference for equal NON-ZERO maxima (exact duplicates: cells with identical coordinates
+    and expression): ``get_optimal_mapping_relationship`` (spateo/alignment/utils.py:157-191) resolves such ties with a
+    KD-tree over the coordinates, here the lowest index in the solver's processing (Morton) order wins. Ties at value 0
+    (rows / columns without any posterior mass) are handled like the reference. Pass a dense ``pi`` to get the reference's
+    tie rule."""
 
     def __init__(self, shape, row_arg, row_val, col_arg, col_val):
         self.shape = tuple(shape)

@@ -94,3 +94,54 @@ def test_morpho_align_ref_carries_the_field_to_the_full_slices():
     assert err.mean() < 1.0, err.mean()
     with pytest.raises(NotImplementedError):
         st.align.morpho_align_ref(models, sampling_method="trn", device="0")
+
+
+def test_pipelined_chain_equals_serial_chain():
+    """align_chain_pipelined (next pair prepared on a second stream under the current pair's EM, iterations replayed from
+    CUDA graphs) gives the transformations of the serial driver and places every slice on slice 0's frame."""
+    import spateo_release_b200 as st
+
+    models, poses = _chain(n_slices=4, n=2200)
+    kw = dict(verbose=False, SVI_mode=False, max_iter=80)
+    np.random.seed(0)
+    tr_serial = st.align.morpho_align_transformation([m.copy() for m in models], device="0", **kw)
+    np.random.seed(0)
+    stats = {}
+    mine = [m.copy() for m in models]
+    placed, tr = st.align.align_chain_pipelined(lambda k: mine[k], 4, device="0", stats=stats, **kw)
+    assert stats["pairs"] == [0, 1, 2] and len(stats["seconds_per_pair"]) == 3 and stats["kernel_launches"] > 0
+    for a, b in zip(tr_serial, tr):
+        assert np.allclose(a["Rotation"], b["Rotation"], atol=1e-5) and np.allclose(a["Translation"], b["Translation"], atol=1e-3)
+    R0, s0 = poses[0]
+    for k in (1, 2, 3):
+        want = np.asarray(placed[k].obsm["truth"]) @ R0.T + s0
+        assert np.abs(np.asarray(placed[k].obsm["align_spatial"]) - want).mean() < 1.0
+    assert np.allclose(placed[0].obsm["align_spatial"], models[0].obsm["spatial"])
+
+
+def test_gather_transformations_under_nccl_resolves_index_strings():
+    """With an NCCL process group the slab must live on the CUDA device even when the package-style device string ("0") or
+    None is passed (round-1 advisor finding); single rank, so no second GPU is needed."""
+    import socket
+
+    import torch
+    import torch.distributed as dist
+
+    from spateo_release_b200.alignment.distributed import gather_transformations
+
+    if dist.is_initialized():
+        pytest.skip("a process group already exists in this process")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK="0", WORLD_SIZE="1")
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+    try:
+        local = {p: {"Rotation": np.eye(2) * (p + 1), "Translation": np.array([p, -p], dtype=float)} for p in range(3)}
+        for dev in ("0", None, "cuda:0"):
+            out = gather_transformations(local, 3, device=dev)
+            assert [float(t["Rotation"][0, 0]) for t in out] == [1.0, 2.0, 3.0]
+            assert np.allclose(out[2]["Translation"], [2.0, -2.0])
+    finally:
+        dist.destroy_process_group()
