@@ -137,6 +137,7 @@ typedef struct spb_em_params {
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
   int32_t* collist;            /* [ldx/ROW_TILE][nbb_pad] per-row-block column work list */
   int32_t* colcount;           /* [ldx/ROW_TILE] list lengths */
+  int32_t* colsplit;           /* [ldx/ROW_TILE] list positions >= colsplit[rb] hold columns whose SPATIAL weights exp(-d/(2 sigma2/variance)) are exactly 0 for the whole row block (they only need the sigma2 / full posteriors) */
   uint32_t* colmask;           /* [nbb_pad][SPB_COLMASK_WORDS] sparse mode: row blocks that can hold a non-zero weight, or NULL */
   double* UtWU;                /* [K][K] accumulator */
   double* UtPXB;               /* [K][3] accumulator */

@@ -954,6 +954,7 @@ class Morpho_pairwise:
         s["bbox"] = torch.zeros((nrb, 8), dtype=f32, device=dev)
         s["collist"] = torch.zeros((nrb, self._nbb_pad), dtype=torch.int32, device=dev)
         s["colcount"] = torch.zeros((nrb,), dtype=torch.int32, device=dev)
+        s["colsplit"] = torch.zeros((nrb,), dtype=torch.int32, device=dev)
         if self.sparse_calculation_mode:
             s["colmask"] = torch.zeros((self._nbb_pad, _capi.CONST["SPB_COLMASK_WORDS"]), dtype=torch.int32, device=dev)
         s["UtWU"] = torch.zeros((K, K), dtype=f64, device=dev)
@@ -1046,7 +1047,7 @@ class Morpho_pairwise:
         p.GT, p.UT = ptr(self._GT).value, ptr(self._UT).value
         for name in ("xa", "xb4", "Gamma", "kappa", "batch_idx", "alpha", "SigmaDiag", "lm", "mm", "VnA", "RnA", "XAHat",
                      "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart",
-                     "rowpart", "bbox", "collist", "colcount", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc",
+                     "rowpart", "bbox", "collist", "colcount", "colsplit", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc",
                      "trace_buf"):
             t = s[name]
             setattr(p, name, None if t is None else t.data_ptr())

@@ -183,6 +183,24 @@ __device__ __forceinline__ RowRegs load_rows(const float* __restrict__ XA, int64
 }
 
 // sweep 1, one pipeline stage: per column the four partial sums of this thread's 4 rows (index v * kColStage + jj)
+// sweep 1, a stage whose columns are "spatially dead" for this row block (exp2(c_s d) flushes to 0 for every pair: the narrow
+// spatial posterior has no mass here): only the two sums of the sigma2 / full posteriors are formed — half the MUFU work.
+template <int kColStage, int kStages, int kDim = 3>
+__device__ __forceinline__ void sweep1_stage_q(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
+                                               u64 CQ, float (&acc)[2 * kColStage]) {
+#pragma unroll
+  for (int jj = 0; jj < kColStage; ++jj) {
+    const ulonglong2 ya = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][0]);
+    const ulonglong2 yb = *reinterpret_cast<const ulonglong2*>(&sm.cols[s][jj][1]);
+    const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
+    const u64 da = sqdist2<kDim>(R.xa0, R.xa1, R.xa2, ya.x, ya.y, yb.x);
+    const u64 db = sqdist2<kDim>(R.xb0, R.xb1, R.xb2, ya.x, ya.y, yb.x);
+    const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
+    acc[0 * kColStage + jj] = hsum(add2(qa, qb));
+    acc[1 * kColStage + jj] = hsum(fma2(qa, g.x, mul2(qb, g.y)));
+  }
+}
+
 template <int kColStage, int kStages, int kDim = 3>
 __device__ __forceinline__ void sweep1_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
                                              u64 CQ, u64 CS, float (&acc)[4 * kColStage]) {
@@ -234,7 +252,8 @@ __device__ __forceinline__ u64 keep_ge(u64 w, float tau) {
   return pk(a >= tau ? a : 0.f, b >= tau ? b : 0.f);
 }
 
-template <int kColStage, int kStages, bool kSparse, int kDim = 3>
+// kSpatial = false: stage of spatially dead columns (see sweep1_stage_q) — K_NA_spatial receives exact zeros from them
+template <int kColStage, int kStages, bool kSparse, int kDim = 3, bool kSpatial = true>
 __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStages>& sm, int s, int tid, const RowRegs& R,
                                              u64 CQ, u64 CS, S2Acc& A) {
 #pragma unroll
@@ -246,10 +265,12 @@ __device__ __forceinline__ void sweep2_stage(const SmemLayoutT<kColStage, kStage
     const ulonglong2 g = *reinterpret_cast<const ulonglong2*>(&sm.tile[s][jj][tid * 4]);
     const u64 da = sqdist2<kDim>(R.xa0, R.xa1, R.xa2, c0.x, c0.y, c1.x);
     const u64 db = sqdist2<kDim>(R.xb0, R.xb1, R.xb2, c0.x, c0.y, c1.x);
-    const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+    if constexpr (kSpatial) {
+      const u64 sa = ex2_2(mul2(CS, da)), sb = ex2_2(mul2(CS, db));
+      A.spa = fma2(sa, c1.y, A.spa);
+      A.spb = fma2(sb, c1.y, A.spb);
+    }
     const u64 qa = ex2_2(fma2(CQ, da, R.lma)), qb = ex2_2(fma2(CQ, db, R.lmb));
-    A.spa = fma2(sa, c1.y, A.spa);
-    A.spb = fma2(sb, c1.y, A.spb);
     const u64 ta = mul2(qa, c2.x), tb = mul2(qb, c2.x);
     A.s2a = add2(A.s2a, ta);
     A.s2b = add2(A.s2b, tb);
@@ -301,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colgeom, const float* __restrict__ XA, const float* __restrict__ lm,
                     const float* __restrict__ mm, const spb_scalars* __restrict__ sc, float* __restrict__ colpart,
-                    int NBb, int nbb_pad, const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
+                    int NBb, int nbb_pad, const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount,
+                    const int32_t* __restrict__ colsplit) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using Smem = SmemLayoutT<kColStage, kStages>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
@@ -311,6 +333,7 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
   const ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
   const int32_t* list = collist + (int64_t)rb * nbb_pad;
   const int32_t* col_index = batch_cols(batch_base, sc, NBb);
+  const int split = colsplit[rb];  // list positions >= split: spatially dead columns
   if (cr.begin >= cr.end) return;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -334,13 +357,38 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     mbar_wait(&sm.full[s], (st / kStages) & 1);
     const int pb = cr.begin + st * kColStage;
     constexpr int NV = 4 * kColStage;  // partial sums per thread per stage, index v * kColStage + jj
+    const int buf = st & 1;
+    if (pb >= split) {
+      // all columns of the stage are spatially dead: sums 0 and 1 are exact zeros, only 2 and 3 are computed and reduced
+      constexpr int NQ = 2 * kColStage;
+      float acc[NQ];
+      sweep1_stage_q<kColStage, kStages, kDim>(sm, s, tid, R, CQ, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.empty[s]);
+      butterfly_reduce<NQ>(acc, lane);
+      constexpr int kShiftQ = (NQ == 32) ? 0 : (NQ == 16 ? 1 : 2);
+      if ((lane & ((1 << kShiftQ) - 1)) == 0) sm.red[buf][warp][lane >> kShiftQ] = acc[0];
+      named_bar_sync(1, kConsumers);
+      if (warp == 0) {
+        if (lane < NQ) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kConsumers / 32; ++w) t += sm.red[buf][w][lane];
+          const int v = 2 + lane / kColStage, jj = lane % kColStage;
+          if (pb + jj < cr.end) colpart[((int64_t)rb * 4 + v) * nbb_pad + list[pb + jj]] = t;
+        } else if (lane < 2 * NQ) {
+          const int v = (lane - NQ) / kColStage, jj = (lane - NQ) % kColStage;
+          if (pb + jj < cr.end) colpart[((int64_t)rb * 4 + v) * nbb_pad + list[pb + jj]] = 0.f;
+        }
+      }
+      continue;
+    }
     float acc[NV];
     sweep1_stage<kColStage, kStages, kDim>(sm, s, tid, R, CQ, CS, acc);
     __syncwarp();
     if (lane == 0) mbar_arrive(&sm.empty[s]);  // stage buffer is free again
     butterfly_reduce<NV>(acc, lane);
     constexpr int kShift = (NV == 32) ? 0 : (NV == 16 ? 1 : 2);  // lane -> value index
-    const int buf = st & 1;
     if ((lane & ((1 << kShift) - 1)) == 0) sm.red[buf][warp][lane >> kShift] = acc[0];
     named_bar_sync(1, kConsumers);
     if (warp == 0 && lane < NV) {
@@ -408,13 +456,15 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks)
 estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __restrict__ batch_base,
                     const float* __restrict__ colconst, const float* __restrict__ XA, const float* __restrict__ lm,
                     const spb_scalars* __restrict__ sc, float* __restrict__ rowpart, int NBb, int nbb_pad,
-                    const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount) {
+                    const int32_t* __restrict__ collist, const int32_t* __restrict__ colcount,
+                    const int32_t* __restrict__ colsplit) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   using Smem = SmemLayoutT<kColStage, kStages>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = blockIdx.x, seg = blockIdx.y;
   const int i0 = rb * kRowTile;
+  const int split = colsplit[rb];  // list positions >= split: spatially dead columns (no spatial-posterior work)
   ColRange cr = col_range<kColStage>(colcount, rb, seg, gridDim.y);
   const int32_t* list = collist + (int64_t)rb * nbb_pad;
   const int32_t* col_index = batch_cols(batch_base, sc, NBb);
@@ -442,7 +492,8 @@ estep_sweep2_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
     const int s = st % kStages;
     if (kDbg != 2 || st < kStages) mbar_wait(&sm.full[s], (st / kStages) & 1);
     if constexpr (kDbg == 1) stream_only_stage<kColStage, kStages>(sm, s, tid, A);
-    else sweep2_stage<kColStage, kStages, kSparse, kDim>(sm, s, tid, R, CQ, CS, A);
+    else if (j_begin + st * kColStage >= split) sweep2_stage<kColStage, kStages, kSparse, kDim, false>(sm, s, tid, R, CQ, CS, A);
+    else sweep2_stage<kColStage, kStages, kSparse, kDim, true>(sm, s, tid, R, CQ, CS, A);
     if constexpr (kDbg != 2) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.empty[s]);
@@ -601,12 +652,13 @@ constexpr int kListThreads = 1024;
 __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
                                                                        int NBb, spb_scalars* __restrict__ sc, int cull,
                                                                        int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
-                                                                       int nbb_pad, uint32_t* __restrict__ colmask,
-                                                                       float* __restrict__ colpart) {
-  extern __shared__ uint32_t keep_bits[];  // one word per 32 columns
-  __shared__ int warp_cnt[32];
+                                                                       int32_t* __restrict__ colsplit, int nbb_pad,
+                                                                       uint32_t* __restrict__ colmask, float* __restrict__ colpart) {
+  extern __shared__ uint32_t keep_bits[];  // [2][nwords]: one word per 32 columns — kept at all | spatially live
+  __shared__ int warp_cnt[2][32];
   const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float cq = sc->c_q * (1.0f - 1e-5f);
+  const float cs = sc->c_s * (1.0f - 1e-5f);  // c_s = c_q * sigma2_variance <= c_q: the spatial weight dies first
   float lo[3], hi[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -614,14 +666,15 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
     hi[d] = bbox[rb * 8 + 3 + d];
   }
   const int nwords = (NBb + 31) / 32;
+  uint32_t* live_bits = keep_bits + nwords;
   const int wpw = (nwords + 31) / 32;  // words per warp
   const int w0 = warp * wpw, w1 = min(nwords, w0 + wpw);
-  int cnt = 0;
+  int cnt = 0, cnt_live = 0;
   for (int wd = w0; wd < w1; ++wd) {
     const int j = wd * 32 + lane;
-    bool keep = false;
+    bool keep = false, live = false;
     if (j < NBb) {
-      keep = true;
+      keep = live = true;
       if (cull) {
         const float* y = colgeom + (int64_t)j * 8;
         float d2 = 0.f;
@@ -632,42 +685,58 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
           d2 = fmaf(g, g, d2);
         }
         keep = cq * d2 >= -127.0f;
+        live = cs * d2 >= -127.0f;  // implies keep
       }
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) keep_bits[wd] = bits;
-    cnt += __popc(bits);
+    const uint32_t bits = __ballot_sync(0xffffffffu, keep), lbits = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) {
+      keep_bits[wd] = bits;
+      live_bits[wd] = lbits;
+    }
+    cnt += __popc(bits & ~lbits);  // kept but spatially dead
+    cnt_live += __popc(lbits);
   }
-  if (lane == 0) warp_cnt[warp] = cnt;
+  if (lane == 0) {
+    warp_cnt[0][warp] = cnt_live;
+    warp_cnt[1][warp] = cnt;
+  }
   __syncthreads();
-  int off = 0, total = 0;
-  {
-    const int c = warp_cnt[lane];
+  int off_live = 0, off_dead = 0, total_live = 0, total_dead = 0;
+#pragma unroll
+  for (int grp = 0; grp < 2; ++grp) {
+    const int c = warp_cnt[grp][lane];
     int inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += v;
     }
-    off = __shfl_sync(0xffffffffu, inc - c, warp);   // exclusive prefix of this warp
-    total = __shfl_sync(0xffffffffu, inc, 31);
+    const int mine = __shfl_sync(0xffffffffu, inc - c, warp);  // exclusive prefix of this warp
+    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+    if (grp == 0) off_live = mine, total_live = tot;
+    else off_dead = mine, total_dead = tot;
   }
+  off_dead += total_live;  // the spatially dead columns follow the live ones in the list
   int32_t* list = collist + (int64_t)rb * nbb_pad;
   for (int wd = w0; wd < w1; ++wd) {
-    const uint32_t bits = keep_bits[wd];
+    const uint32_t bits = keep_bits[wd], lbits = live_bits[wd], dbits = bits & ~lbits;
     const int j = wd * 32 + lane;
-    if ((bits >> lane) & 1u) {
-      list[off + __popc(bits & ((1u << lane) - 1u))] = j;
-      if (colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS) atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
-    } else if (j < NBb) {
+    const uint32_t below = (1u << lane) - 1u;
+    if ((lbits >> lane) & 1u) list[off_live + __popc(lbits & below)] = j;
+    else if ((dbits >> lane) & 1u) list[off_dead + __popc(dbits & below)] = j;
+    else if (j < NBb) {
 #pragma unroll
       for (int v = 0; v < 4; ++v) colpart[((int64_t)rb * 4 + v) * nbb_pad + j] = 0.f;
     }
-    off += __popc(bits);
+    if (((bits >> lane) & 1u) && colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS)
+      atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
+    off_live += __popc(lbits);
+    off_dead += __popc(dbits);
   }
   if (threadIdx.x == 0) {
-    colcount[rb] = total;
-    atomicAdd(&sc->visited, (double)total);
+    colcount[rb] = total_live + total_dead;
+    colsplit[rb] = total_live;
+    atomicAdd(&sc->visited, (double)(total_live + total_dead));
   }
 }
 
@@ -1068,7 +1137,7 @@ int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   }
   dim3 grid(p->ldx / kRowTile, p->seg1);
   estep_sweep1_kernel<C, S, B, DIM><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colgeom, p->XAHat, p->lm, p->mm, p->sc,
-                                                                  p->colpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
+                                                                  p->colpart, p->NBb, p->nbb_pad, p->collist, p->colcount, p->colsplit);
   return 0;
 }
 
@@ -1084,7 +1153,7 @@ int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   }
   dim3 grid(p->ldx / kRowTile, p->seg2);
   estep_sweep2_kernel<C, S, B, SP, DBG, DIM><<<grid, kThreads, sizeof(Smem), st>>>(p->GT, p->ldx, bidx, p->colconst, p->XAHat, p->lm, p->sc,
-                                                                  p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount);
+                                                                  p->rowpart, p->NBb, p->nbb_pad, p->collist, p->colcount, p->colsplit);
   return 0;
 }
 
@@ -1119,8 +1188,8 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
     cudaError_t e = cudaMemsetAsync(colmask, 0, sizeof(uint32_t) * SPB_COLMASK_WORDS * (size_t)p->nbb_pad, (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
   }
-  const size_t smem = sizeof(uint32_t) * (size_t)((p->NBb + 31) / 32);
-  if (smem > 200 * 1024) return SPB_EUNSUPPORTED;  // 1.6 M columns per iteration
+  const size_t smem = 2 * sizeof(uint32_t) * (size_t)((p->NBb + 31) / 32);
+  if (smem > 200 * 1024) return SPB_EUNSUPPORTED;  // 800 k columns per iteration
   static bool attr_set[SPB_MAX_DEVICES] = {};
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
@@ -1129,7 +1198,7 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
     attr_set[dev_] = true;
   }
   build_col_lists_kernel<<<nrb, kListThreads, smem, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
-                                                                            p->colcount, p->nbb_pad, colmask, p->colpart);
+                                                                            p->colcount, p->colsplit, p->nbb_pad, colmask, p->colpart);
   SPB_CHECK_LAUNCH();
   return 0;
 }
