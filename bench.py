@@ -825,6 +825,12 @@ def main():
         "sweep1_GBs": s1_gbs, "sweep2_GBs": s2_gbs,
         "visited_pair_fraction": float(vis.sum() / (tiles_all * vis.size)),
         "sweeps_share_of_step": float(sw.sum() / sw.shape[0] / main_ev["ms"]),
+        # where the time goes over the run: mean (sweep 1, sweep 2) ms per iteration and visited fraction per quarter
+        "by_quarter": [
+            {"iterations": f"{a}-{b - 1}", "sweep1_ms": float(sw[:, a:b, 0].mean()), "sweep2_ms": float(sw[:, a:b, 1].mean()),
+             "visited_pair_fraction": float(vis[:, a:b].mean() / tiles_all)}
+            for a, b in ((q * sw.shape[1] // 4, (q + 1) * sw.shape[1] // 4) for q in range(4)) if b > a
+        ],
         "dense": {
             "note": "same kernels with culling off: every launch reads all N_A x N_B pairs (4 B each)",
             "value": pairs_per_step * world / (dense_arm["ms"] * 1e-3), "ms_per_step": dense_arm["ms"],

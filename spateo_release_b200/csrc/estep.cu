@@ -670,31 +670,44 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
   const int wpw = (nwords + 31) / 32;  // words per warp
   const int w0 = warp * wpw, w1 = min(nwords, w0 + wpw);
   int cnt = 0, cnt_live = 0;
-  for (int wd = w0; wd < w1; ++wd) {
-    const int j = wd * 32 + lane;
-    bool keep = false, live = false;
-    if (j < NBb) {
-      keep = live = true;
-      if (cull) {
-        const float* y = colgeom + (int64_t)j * 8;
-        float d2 = 0.f;
+  constexpr int kU = 4;  // words per trip: the 12 coordinate loads of a trip are independent (the loop is latency-bound)
+  for (int wb = w0; wb < w1; wb += kU) {
+    float yy[kU][3];
 #pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float yd = y[2 * d];
-          const float g = fmaxf(fmaxf(lo[d] - yd, yd - hi[d]), 0.f);
-          d2 = fmaf(g, g, d2);
+    for (int u = 0; u < kU; ++u) {
+      const int j = (wb + u) * 32 + lane;
+      const bool in = (wb + u < w1) && j < NBb;
+      const float* y = colgeom + (int64_t)(in ? j : 0) * 8;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) yy[u][d] = cull ? y[2 * d] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int wd = wb + u;
+      if (wd >= w1) break;  // warp-uniform
+      const int j = wd * 32 + lane;
+      bool keep = false, live = false;
+      if (j < NBb) {
+        keep = live = true;
+        if (cull) {
+          float d2 = 0.f;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const float g = fmaxf(fmaxf(lo[d] - yy[u][d], yy[u][d] - hi[d]), 0.f);
+            d2 = fmaf(g, g, d2);
+          }
+          keep = cq * d2 >= -127.0f;
+          live = cs * d2 >= -127.0f;  // implies keep
         }
-        keep = cq * d2 >= -127.0f;
-        live = cs * d2 >= -127.0f;  // implies keep
       }
+      const uint32_t bits = __ballot_sync(0xffffffffu, keep), lbits = __ballot_sync(0xffffffffu, live);
+      if (lane == 0) {
+        keep_bits[wd] = bits;
+        live_bits[wd] = lbits;
+      }
+      cnt += __popc(bits & ~lbits);  // kept but spatially dead
+      cnt_live += __popc(lbits);
     }
-    const uint32_t bits = __ballot_sync(0xffffffffu, keep), lbits = __ballot_sync(0xffffffffu, live);
-    if (lane == 0) {
-      keep_bits[wd] = bits;
-      live_bits[wd] = lbits;
-    }
-    cnt += __popc(bits & ~lbits);  // kept but spatially dead
-    cnt_live += __popc(lbits);
   }
   if (lane == 0) {
     warp_cnt[0][warp] = cnt_live;
