@@ -555,10 +555,10 @@ def run_shard(args):
         barrier()
         t_prep = time.perf_counter() - t0
         ms = []
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank) if clocks is None else None  # clocks are sampled during the first mode's timed steps
         for s in range(args.warmup + args.steps):
             m.reset_state()
-            if s == args.warmup and mode != "nccl" or (s == args.warmup and world == 1):
+            if s == args.warmup and sampler is not None:
                 sampler.start()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -568,7 +568,7 @@ def run_shard(args):
             barrier()
             if s >= args.warmup:
                 ms.append(max_over_ranks(e0.elapsed_time(e1)))
-        if sampler.proc is not None:
+        if sampler is not None:
             clocks = sampler.stop()
         m._finish()
         results[mode] = {"ms_per_step": float(np.mean(ms)), "mode_used": m._shard_mode, "prepare_s": max_over_ranks(t_prep),
