@@ -406,53 +406,54 @@ __global__ void __launch_bounds__(256) nonrigid_solve_kernel(spb_em_params p) {
       __syncthreads();
     }
     if (s_off <= 1e-30 * s_diag || s_off == 0.0) break;
-    for (int stp = 0; stp < Kp - 1; ++stp) {
+    // One sweep = Kp - 1 rounds of Kp / 2 disjoint pairs (round-robin tournament: index Kp - 1 stays, the others rotate; the
+    // pairs of a round follow from the round number alone). A round is TWO barrier-separated phases: the rotations from the
+    // current matrix, then A <- J^T A J in one pass over 2 x 2 blocks (block (a, b) = rows of pair a x columns of pair b only
+    // touches its own four entries, so rows and columns need no barrier in between) together with V <- V J.
+    const int m = Kp - 1;
+    for (int stp = 0; stp < m; ++stp) {
+      auto pair_of = [&](int i, int& pp, int& qq) {
+        const int x = i == 0 ? stp % m : (stp + i) % m;
+        const int y = i == 0 ? m : (stp - i + m) % m;
+        pp = min(x, y);
+        qq = max(x, y);
+      };
       if (tid < npair) {
-        const int pp = min(top[tid], bot[tid]), qq = max(top[tid], bot[tid]);
+        int pp, qq;
+        pair_of(tid, pp, qq);
         const double apq = A[pp * Kp + qq];
-        double c = 1.0, s = 0.0;
+        double c = 1.0, sn = 0.0;
         if (fabs(apq) > 1e-300) {
           const double theta = (A[qq * Kp + qq] - A[pp * Kp + pp]) / (2.0 * apq);
           const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
           c = 1.0 / sqrt(t * t + 1.0);
-          s = t * c;
+          sn = t * c;
         }
         cs[2 * tid] = c;
-        cs[2 * tid + 1] = s;
+        cs[2 * tid + 1] = sn;
+        top[tid] = pp;  // the round's pairs, for the update phase
+        bot[tid] = qq;
       }
       __syncthreads();
-      // rows: A <- J^T A
-      for (int q = tid; q < npair * Kp; q += nt) {
-        const int pr = q / Kp, k = q % Kp;
-        const int pp = min(top[pr], bot[pr]), qq = max(top[pr], bot[pr]);
-        const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double ap = A[pp * Kp + k], aq = A[qq * Kp + k];
-        A[pp * Kp + k] = c * ap - s * aq;
-        A[qq * Kp + k] = s * ap + c * aq;
+      for (int q = tid; q < npair * npair; q += nt) {
+        const int pa = q / npair, pb = q % npair;
+        const int p0 = top[pa], q0 = bot[pa], r0 = top[pb], t0 = bot[pb];
+        const double ca = cs[2 * pa], sa = cs[2 * pa + 1], cb = cs[2 * pb], sb = cs[2 * pb + 1];
+        const double apr = A[p0 * Kp + r0], apt = A[p0 * Kp + t0], aqr = A[q0 * Kp + r0], aqt = A[q0 * Kp + t0];
+        const double xpr = ca * apr - sa * aqr, xpt = ca * apt - sa * aqt;  // rows: J_a^T A
+        const double xqr = sa * apr + ca * aqr, xqt = sa * apt + ca * aqt;
+        A[p0 * Kp + r0] = cb * xpr - sb * xpt;                              // columns: (.) J_b
+        A[p0 * Kp + t0] = sb * xpr + cb * xpt;
+        A[q0 * Kp + r0] = cb * xqr - sb * xqt;
+        A[q0 * Kp + t0] = sb * xqr + cb * xqt;
       }
-      __syncthreads();
-      // columns: A <- A J, V <- V J
       for (int q = tid; q < npair * Kp; q += nt) {
         const int pr = q / Kp, k = q % Kp;
-        const int pp = min(top[pr], bot[pr]), qq = max(top[pr], bot[pr]);
-        const double c = cs[2 * pr], s = cs[2 * pr + 1];
-        const double ap = A[k * Kp + pp], aq = A[k * Kp + qq];
-        A[k * Kp + pp] = c * ap - s * aq;
-        A[k * Kp + qq] = s * ap + c * aq;
+        const int pp = top[pr], qq = bot[pr];
+        const double c = cs[2 * pr], sn = cs[2 * pr + 1];
         const double vp = V[k * Kp + pp], vq = V[k * Kp + qq];
-        V[k * Kp + pp] = c * vp - s * vq;
-        V[k * Kp + qq] = s * vp + c * vq;
-      }
-      __syncthreads();
-      // round-robin tournament rotation of the index sets
-      if (tid == 0) {
-        const int last_top = top[npair - 1];
-        const int first_bot = bot[0];
-        for (int q = npair - 1; q >= 2; --q) top[q] = top[q - 1];
-        if (npair > 1) top[1] = first_bot;
-        for (int q = 0; q < npair - 1; ++q) bot[q] = bot[q + 1];
-        bot[npair - 1] = last_top;
-        if (npair == 1) { /* single pair: nothing to rotate */ bot[0] = first_bot; }
+        V[k * Kp + pp] = c * vp - sn * vq;
+        V[k * Kp + qq] = sn * vp + c * vq;
       }
       __syncthreads();
     }
