@@ -649,7 +649,10 @@ __global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restri
 // bits go to shared memory), one block barrier turns the per-warp counts into offsets, pass 2 scatters. The partial column
 // sums of the DROPPED (row block, column) combinations are zeroed here, so sweep 1 needs no 157 MB memset per iteration.
 constexpr int kListThreads = 1024;
-__global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ colgeom,
+// geom: one record per column, `gstride` floats apart, coordinate d at float offset d * gstep (the 16-byte xb4 records when the
+// columns are all fixed cells: half the L2 traffic of the duplicated colgeom layout, which every row block re-reads in full)
+__global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const float* __restrict__ bbox, const float* __restrict__ geom,
+                                                                       int gstride, int gstep,
                                                                        int NBb, spb_scalars* __restrict__ sc, int cull,
                                                                        int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
                                                                        int32_t* __restrict__ colsplit, int nbb_pad,
@@ -677,9 +680,14 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
     for (int u = 0; u < kU; ++u) {
       const int j = (wb + u) * 32 + lane;
       const bool in = (wb + u < w1) && j < NBb;
-      const float* y = colgeom + (int64_t)(in ? j : 0) * 8;
+      const float* y = geom + (int64_t)(in ? j : 0) * gstride;
+      if (gstride == 4) {  // one 16-byte load per column
+        const float4 v = cull ? *reinterpret_cast<const float4*>(y) : make_float4(0.f, 0.f, 0.f, 0.f);
+        yy[u][0] = v.x, yy[u][1] = v.y, yy[u][2] = v.z;
+      } else {
 #pragma unroll
-      for (int d = 0; d < 3; ++d) yy[u][d] = cull ? y[2 * d] : 0.f;
+        for (int d = 0; d < 3; ++d) yy[u][d] = cull ? y[d * gstep] : 0.f;
+      }
     }
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
@@ -1210,8 +1218,10 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
-  build_col_lists_kernel<<<nrb, kListThreads, smem, (cudaStream_t)stream>>>(p->bbox, p->colgeom, p->NBb, p->sc, p->cull, p->collist,
-                                                                            p->colcount, p->colsplit, p->nbb_pad, colmask, p->colpart);
+  const bool all_cols = !(p->svi && p->batch_idx);  // the iteration's columns are the fixed cells themselves, in order
+  build_col_lists_kernel<<<nrb, kListThreads, smem, (cudaStream_t)stream>>>(
+      p->bbox, all_cols ? p->xb4 : p->colgeom, all_cols ? 4 : 8, all_cols ? 1 : 2, p->NBb, p->sc, p->cull, p->collist, p->colcount,
+      p->colsplit, p->nbb_pad, colmask, p->colpart);
   SPB_CHECK_LAUNCH();
   return 0;
 }
