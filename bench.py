@@ -791,7 +791,7 @@ def main():
     except Exception:
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    nrb = m.ldx // 1024
+    nrb = m.ldx // _capi.ROW_TILE
     tiles_all = float(nrb) * cols
     # algorithmic bytes of one sweep launch = 4 B x (cell pairs the launch has to read): all pairs when dense, the visited
     # (row block x column) tiles x N_A/nrb rows when culling skipped the provably-zero tiles

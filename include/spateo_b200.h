@@ -12,7 +12,7 @@
  * SPB_E* code, and never synchronise the device unless documented. float = IEEE fp32, accumulators are fp64.
  *
  * Layout vocabulary (moving slice A = rows i, fixed slice B = columns j):
- *   ldx          row pitch: N_A rounded up to SPB_ROW_TILE (1024). Per-row vectors are length ldx.
+ *   ldx          row pitch: N_A rounded up to SPB_ROW_TILE. Per-row vectors are length ldx.
  *   xa / XAHat   [3][ldx] structure-of-arrays coordinates (unused dims = 0; pad rows i >= N_A hold 1e18).
  *   xb4          [N_B][4] fixed-slice coordinates (y0,y1,y2,0).
  *   GT           [N_B][ldx] expression-probability matrix g_ij stored COLUMN-OF-P-major (one contiguous row per
@@ -28,12 +28,12 @@
 extern "C" {
 #endif
 
-#define SPB_ROW_TILE 1024
+#define SPB_ROW_TILE 512
 #define SPB_COL_STAGE 8
 #define SPB_COLCONST_FLOATS 20 /* per-column constant record of sweep 2 (see spb_em_params.colconst) */
 #define SPB_MAX_K_FUSED 64 /* largest K solved by the in-library Jacobi kernel */
 #define SPB_TRACE_STRIDE 8
-#define SPB_COLMASK_WORDS 8 /* per-column bit mask over row blocks (sparse mode): up to 256 row blocks = 262,144 rows */
+#define SPB_COLMASK_WORDS 16 /* per-column bit mask over row blocks (sparse mode): up to 512 row blocks = 262,144 rows */
 
 #define SPB_EINVAL (-2)
 #define SPB_EUNSUPPORTED (-3)
@@ -133,6 +133,7 @@ typedef struct spb_em_params {
   float* colgeom;              /* [nbb_pad][8] (y0,y0,y1,y1,y2,y2,0,0): this iteration's columns, duplicated for f32x2 */
   float* colconst;             /* [nbb_pad][SPB_COLCONST_FLOATS] (y0,y0,y1,y1, y2,y2,a,a, b,b,c,c, cy0,cy0,cy1,cy1, cy2,cy2,tau,tau); zero beyond NBb */
   float* colpart;              /* [ldx/ROW_TILE][4][nbb_pad] partial column sums */
+  uint32_t* keepmask;          /* [ldx/ROW_TILE][(nbb_pad+31)/32] bit j of row rb: column j is on rb's work list, i.e. colpart[rb][.][j] is live */
   float* rowpart;              /* [seg2][8][ldx] partial row statistics */
   float* bbox;                 /* [ldx/ROW_TILE][8] bounding box (lo0,lo1,lo2,hi0,hi1,hi2) of each row block's XAHat */
   int32_t* collist;            /* [ldx/ROW_TILE][nbb_pad] per-row-block column work list */
@@ -223,7 +224,7 @@ int spb_label_cost(const int32_t* labA, const int32_t* labB, const float* LT, in
                    int32_t accumulate, float* GT, int64_t ldx, void* stream); /* utils.py:830 */
 
 /* ---- E-step: calc_distance(euc) + get_P_core + row/col sums, P never materialised ---------------------------- */
-/* pipeline shape of the two sweep kernels: 0 = 8 columns x 3 stages (2 CTAs/SM), 1 = 4 x 4 (3 CTAs/SM), 2 = 4 x 6 */
+/* diagnostics of the two sweep kernels: cfg = 16 * mode, mode 0 = product, 1 = stream only, 2 = arithmetic only (profiles/sweep_micro.py) */
 int spb_set_sweep_config(int32_t cfg);
 int spb_gather_cols(const spb_em_params* p, int32_t iter, void* stream);   /* morpho_class.py:1149 */
 /* row-block bounding boxes + per-block column work lists (exact zero-tile culling when p->cull) — new, no reference line */

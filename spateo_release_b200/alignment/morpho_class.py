@@ -894,13 +894,14 @@ class Morpho_pairwise:
 
     @staticmethod
     def _choose_segments(nrb: int, nbb: int) -> int:
-        """Column segments so that CTAs ~ a multiple of 2 x 148 and a segment is at most ``SPB_MAX_COLS_PER_CTA`` columns
+        """Column segments so that CTAs ~ a multiple of the resident CTA slots (148 SMs x 2048 / ROW_TILE) and a segment is at most ``SPB_MAX_COLS_PER_CTA`` columns
         (short CTAs keep the tail of the last wave small once culling has shortened the column lists)."""
         cap = int(os.environ.get("SPB_MAX_COLS_PER_CTA", "4096"))
         max_seg = max(1, nbb // _capi.COL_STAGE)
+        slots = 148 * (2048 // _capi.ROW_TILE)  # resident CTAs of the sweeps on one B200
         seg = 1
         for waves in range(1, 256):
-            seg = max(1, min(max_seg, (296 * waves) // max(nrb, 1)))
+            seg = max(1, min(max_seg, (slots * waves) // max(nrb, 1)))
             if (nbb + seg - 1) // seg <= cap or seg == max_seg:
                 break
         return seg
@@ -947,6 +948,7 @@ class Morpho_pairwise:
         s["colgeom"] = torch.zeros((self._nbb_pad, 8), dtype=f32, device=dev)
         s["colconst"] = torch.zeros((self._nbb_pad, _capi.CONST["SPB_COLCONST_FLOATS"]), dtype=f32, device=dev)
         s["colpart"] = torch.zeros((nrb, 4, self._nbb_pad), dtype=f32, device=dev)
+        s["keepmask"] = torch.zeros((nrb, (self._nbb_pad + 31) // 32), dtype=torch.int32, device=dev)
         seg1 = self._choose_segments(nrb, nbb)
         seg2 = self._choose_segments(nrb, nbb)
         seg_alloc = max(seg2, self._choose_segments(nrb, nbb_alloc))
@@ -1046,7 +1048,7 @@ class Morpho_pairwise:
                 setattr(p, name, s[name].data_ptr())
         p.GT, p.UT = ptr(self._GT).value, ptr(self._UT).value
         for name in ("xa", "xb4", "Gamma", "kappa", "batch_idx", "alpha", "SigmaDiag", "lm", "mm", "VnA", "RnA", "XAHat",
-                     "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart",
+                     "K_NA", "K_NA_spatial", "K_NA_sigma2", "PXB", "PXB_term", "K_NB", "colgeom", "colconst", "colpart", "keepmask",
                      "rowpart", "bbox", "collist", "colcount", "colsplit", "UtWU", "UtPXB", "SigmaInv", "Sigma", "Coff", "moments", "sc",
                      "trace_buf"):
             t = s[name]

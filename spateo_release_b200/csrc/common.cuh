@@ -7,7 +7,6 @@
 
 #include "../../include/spateo_b200.h"
 
-#define SPB_THREADS 256 /* consumer threads per CTA in the streaming kernels (4 rows each) */
 #define SPB_STAGES 3
 
 extern "C" int64_t spb_launch_count(void);

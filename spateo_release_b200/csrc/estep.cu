@@ -17,9 +17,10 @@
 
 namespace {
 
-constexpr int kRowTile = SPB_ROW_TILE;   // 1024 rows per CTA
-constexpr int kConsumers = SPB_THREADS;  // 256
+constexpr int kRowTile = SPB_ROW_TILE;    // rows per CTA
+constexpr int kConsumers = kRowTile / 4;  // consumer threads, 4 consecutive rows each
 constexpr int kThreads = kConsumers + 32;
+constexpr int kCtas = 2048 / kRowTile;    // resident CTAs per SM the sweeps are built for (96 registers, ~100 KB of shared memory per 1024 rows)
 constexpr int kColF4 = SPB_COLCONST_FLOATS / 4;  // float4 per column constant record (sweep 1 uses the first two)
 
 // Pipeline shape: kColStage columns per stage, kStages stages (compile-time variants, chosen by spb_set_sweep_config).
@@ -408,16 +409,36 @@ estep_sweep1_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __
 // row-block partials per column is a chain of dependent loads otherwise) and combine through shared memory in fp64.
 constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(32 * kFinWarps)
-col_finalize_kernel(const float* __restrict__ colpart, int nrb, int nbb_pad, int NBb, const float* __restrict__ colgeom,
+col_finalize_kernel(const float* __restrict__ colpart, const uint32_t* __restrict__ keepmask, int kstride, int nrb, int nbb_pad,
+                    int NBb, const float* __restrict__ colgeom,
                     const spb_scalars* __restrict__ sc, float* __restrict__ colconst, float* __restrict__ K_NB) {
   __shared__ double part[kFinWarps][4][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   double C[4] = {0, 0, 0, 0};
-  if (j < NBb) {
-    for (int rb = warp; rb < nrb; rb += kFinWarps) {
+  // a (row block, column) partial exists only if the column is on the row block's list; the others are never written or read
+  // (this warp's row blocks: warp, warp + kFinWarps, ...; lane t fetches the mask word of the t-th one, the words are then
+  // broadcast, and four row blocks' loads are in flight before the first add: the fold stays in row-block order)
+  const int nmine = (nrb - warp + kFinWarps - 1) / kFinWarps;
+  for (int base = 0; base < nmine; base += 32) {
+    const int t = base + lane;
+    const uint32_t mymask = t < nmine ? keepmask[(int64_t)(warp + t * kFinWarps) * kstride + blockIdx.x] : 0u;
+    const int cnt = min(32, nmine - base);
+    for (int u0 = 0; u0 < cnt; u0 += 4) {
+      float tmp[4][4];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) C[v] += (double)colpart[((int64_t)rb * 4 + v) * nbb_pad + j];
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bits = __shfl_sync(0xffffffffu, mymask, (u0 + u) & 31);
+        const bool on = (u0 + u < cnt) && ((bits >> lane) & 1u);
+        const int rb = warp + (base + u0 + u) * kFinWarps;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) tmp[u][v] = on ? colpart[((int64_t)rb * 4 + v) * nbb_pad + j] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) C[v] += (double)tmp[u][v];
+      }
     }
   }
 #pragma unroll
@@ -605,9 +626,9 @@ row_stats_p2p_kernel(const uint64_t* __restrict__ peer_stat, int parity, int ran
 }
 
 // bounding box of the current positions of each row block (valid rows only)
-__global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restrict__ XA, int ldx, int NA,
-                                                           float* __restrict__ bbox) {
-  __shared__ float red[6][8];
+__global__ void __launch_bounds__(kConsumers) block_bounds_kernel(const float* __restrict__ XA, int ldx, int NA,
+                                                                  float* __restrict__ bbox) {
+  __shared__ float red[6][kConsumers / 32];
   const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
   for (int q = 0; q < 4; ++q) {
@@ -636,7 +657,7 @@ __global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restri
   __syncthreads();
   if (threadIdx.x < 6) {
     float v = red[threadIdx.x][0];
-    for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
+    for (int w = 1; w < kConsumers / 32; ++w) v = threadIdx.x < 3 ? fminf(v, red[threadIdx.x][w]) : fmaxf(v, red[threadIdx.x][w]);
     bbox[rb * 8 + threadIdx.x] = v;
   }
 }
@@ -646,8 +667,9 @@ __global__ void __launch_bounds__(256) block_bounds_kernel(const float* __restri
 // y_j to the block's bounding box: then ex2(c_q d + lm) and ex2(c_s d) flush to +0 for every pair of the block (lm <= 0,
 // c_s <= c_q < 0), so the dropped pairs would have added exact zeros.
 // One CTA per row block, 32 warps, each warp owns a contiguous range of columns: pass 1 evaluates the test once (the keep
-// bits go to shared memory), one block barrier turns the per-warp counts into offsets, pass 2 scatters. The partial column
-// sums of the DROPPED (row block, column) combinations are zeroed here, so sweep 1 needs no 157 MB memset per iteration.
+// bits go to shared memory), one block barrier turns the per-warp counts into offsets, pass 2 scatters. The keep bits are also
+// published (keepmask): col_finalize folds only the partial column sums that sweep 1 wrote, so the dropped (row block, column)
+// combinations are neither zeroed (a 157-313 MB write per iteration) nor read.
 constexpr int kListThreads = 1024;
 // geom: one record per column, `gstride` floats apart, coordinate d at float offset d * gstep (the 16-byte xb4 records when the
 // columns are all fixed cells: half the L2 traffic of the duplicated colgeom layout, which every row block re-reads in full)
@@ -656,7 +678,8 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
                                                                        int NBb, spb_scalars* __restrict__ sc, int cull,
                                                                        int32_t* __restrict__ collist, int32_t* __restrict__ colcount,
                                                                        int32_t* __restrict__ colsplit, int nbb_pad,
-                                                                       uint32_t* __restrict__ colmask, float* __restrict__ colpart) {
+                                                                       uint32_t* __restrict__ colmask, uint32_t* __restrict__ keepmask,
+                                                                       int kstride) {
   extern __shared__ uint32_t keep_bits[];  // [2][nwords]: one word per 32 columns — kept at all | spatially live
   __shared__ int warp_cnt[2][32];
   const int rb = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -745,10 +768,7 @@ __global__ void __launch_bounds__(kListThreads) build_col_lists_kernel(const flo
     const uint32_t below = (1u << lane) - 1u;
     if ((lbits >> lane) & 1u) list[off_live + __popc(lbits & below)] = j;
     else if ((dbits >> lane) & 1u) list[off_dead + __popc(dbits & below)] = j;
-    else if (j < NBb) {
-#pragma unroll
-      for (int v = 0; v < 4; ++v) colpart[((int64_t)rb * 4 + v) * nbb_pad + j] = 0.f;
-    }
+    if (lane == 0) keepmask[(int64_t)rb * kstride + wd] = bits;  // col_finalize folds only the listed (row block, column) partials
     if (((bits >> lane) & 1u) && colmask != nullptr && rb < 32 * SPB_COLMASK_WORDS)
       atomicOr(colmask + (int64_t)j * SPB_COLMASK_WORDS + (rb >> 5), 1u << (rb & 31));
     off_live += __popc(lbits);
@@ -1144,7 +1164,6 @@ row_argmax_kernel(const float* __restrict__ GT, int64_t ldx, const int32_t* __re
 }
 
 int g_sweep_dbg = 0;  // 0 product, 1 stream-only sweep 2, 2 arithmetic-only sweep 2 (diagnostics, spb_set_sweep_config(16 * mode + cfg))
-int g_sweep_cfg = 0;  // 0: 8 cols x 3 stages, 2 CTAs/SM   1: 4 cols x 4 stages, 3 CTAs/SM   2: 4 cols x 6 stages, 2 CTAs/SM
 
 template <int C, int S, int B, int DIM = 3>
 int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) {
@@ -1153,6 +1172,8 @@ int launch_sweep1(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(estep_sweep1_kernel<C, S, B, DIM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
@@ -1169,6 +1190,8 @@ int launch_sweep2(const spb_em_params* p, const int32_t* bidx, cudaStream_t st) 
   const int dev_ = spb_current_device();
   if (!attr_set[dev_]) {
     cudaError_t e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP, DBG, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(estep_sweep2_kernel<C, S, B, SP, DBG, DIM>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev_] = true;
   }
@@ -1193,15 +1216,14 @@ extern "C" int spb_gather_cols(const spb_em_params* p, int32_t iter, void* strea
 
 extern "C" int spb_set_sweep_config(int32_t cfg) {
   const int shape = cfg & 15, dbg = (cfg >> 4) & 15;
-  if (cfg < 0 || shape > 2 || dbg > 2) return SPB_EINVAL;
-  g_sweep_cfg = shape;
+  if (cfg < 0 || shape != 0 || dbg > 2) return SPB_EINVAL;  // one ring shape is built (8 columns x 3 stages); the others lost
   g_sweep_dbg = dbg;
   return 0;
 }
 
 extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
   const int nrb = p->ldx / kRowTile;
-  block_bounds_kernel<<<nrb, 256, 0, (cudaStream_t)stream>>>(p->XAHat, p->ldx, p->NA, p->bbox);
+  block_bounds_kernel<<<nrb, kConsumers, 0, (cudaStream_t)stream>>>(p->XAHat, p->ldx, p->NA, p->bbox);
   SPB_CHECK_LAUNCH();
   // sparse mode also records, per column, which row blocks can hold a non-zero weight (col_select skips the others)
   uint32_t* colmask = (p->sparse_k > 0 && nrb <= 32 * SPB_COLMASK_WORDS) ? p->colmask : nullptr;
@@ -1221,19 +1243,16 @@ extern "C" int spb_estep_col_lists(const spb_em_params* p, void* stream) {
   const bool all_cols = !(p->svi && p->batch_idx);  // the iteration's columns are the fixed cells themselves, in order
   build_col_lists_kernel<<<nrb, kListThreads, smem, (cudaStream_t)stream>>>(
       p->bbox, all_cols ? p->xb4 : p->colgeom, all_cols ? 4 : 8, all_cols ? 1 : 2, p->NBb, p->sc, p->cull, p->collist, p->colcount,
-      p->colsplit, p->nbb_pad, colmask, p->colpart);
+      p->colsplit, p->nbb_pad, colmask, p->keepmask, (p->nbb_pad + 31) / 32);
   SPB_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
-  // partial column sums of (row block, column) combinations that are not visited read as zero: spb_estep_col_lists zeroes
-  // exactly those entries, every other entry is overwritten by this launch
-  if (g_sweep_cfg == 1) rc = launch_sweep1<4, 4, 3>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 2) rc = launch_sweep1<4, 6, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (p->D == 2) rc = launch_sweep1<8, 3, 2, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else rc = launch_sweep1<8, 3, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  // writes the partial column sums of every (row block, listed column) combination; col_finalize reads exactly those (keepmask)
+  if (p->D == 2) rc = launch_sweep1<8, 3, kCtas, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else rc = launch_sweep1<8, 3, kCtas>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   if (rc) return rc;
   SPB_CHECK_LAUNCH();
   return 0;
@@ -1241,21 +1260,19 @@ extern "C" int spb_estep_sweep1(const spb_em_params* p, int32_t iter, void* stre
 
 extern "C" int spb_col_finalize(const spb_em_params* p, void* stream) {
   col_finalize_kernel<<<(p->NBb + 31) / 32, 32 * kFinWarps, 0, (cudaStream_t)stream>>>(
-      p->colpart, p->ldx / kRowTile, p->nbb_pad, p->NBb, p->colgeom, p->sc, p->colconst, p->K_NB);
+      p->colpart, p->keepmask, (p->nbb_pad + 31) / 32, p->ldx / kRowTile, p->nbb_pad, p->NBb, p->colgeom, p->sc, p->colconst, p->K_NB);
   SPB_CHECK_LAUNCH();
   return 0;
 }
 
 extern "C" int spb_estep_sweep2(const spb_em_params* p, int32_t iter, void* stream) {
   int rc;
-  if (p->sparse_k > 0 && p->D == 2) rc = launch_sweep2<8, 3, 2, true, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (p->sparse_k > 0) rc = launch_sweep2<8, 3, 2, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_dbg == 1) rc = launch_sweep2<8, 3, 2, false, 1>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_dbg == 2) rc = launch_sweep2<8, 3, 2, false, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 1) rc = launch_sweep2<4, 4, 3, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (g_sweep_cfg == 2) rc = launch_sweep2<4, 6, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else if (p->D == 2) rc = launch_sweep2<8, 3, 2, false, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
-  else rc = launch_sweep2<8, 3, 2, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  if (p->sparse_k > 0 && p->D == 2) rc = launch_sweep2<8, 3, kCtas, true, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (p->sparse_k > 0) rc = launch_sweep2<8, 3, kCtas, true>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_dbg == 1) rc = launch_sweep2<8, 3, kCtas, false, 1>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (g_sweep_dbg == 2) rc = launch_sweep2<8, 3, kCtas, false, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else if (p->D == 2) rc = launch_sweep2<8, 3, kCtas, false, 0, 2>(p, batch_ptr(p, iter), (cudaStream_t)stream);
+  else rc = launch_sweep2<8, 3, kCtas, false>(p, batch_ptr(p, iter), (cudaStream_t)stream);
   if (rc) return rc;
   SPB_CHECK_LAUNCH();
   return 0;
