@@ -287,7 +287,10 @@ int spb_rbf_kernel_T(const float* x, int64_t n, int64_t ldx, const float* z, int
 int spb_field_eval(const double* q, int64_t n, int32_t D, const double* z, const double* Coff, int32_t K, double beta,
                    double* out, void* stream); /* transform.py:93,103; gaussian_process.py:109,117 */
 
-/* Descriptor of a fitted field (the vecfld dict of morpho_class.py:1499-1528, host side; passed by value). */
+/* Descriptor of a fitted field (the vecfld dict of morpho_class.py:1499-1528, host side; passed by value).
+   velocity_divisor: 10000 for the Gaussian-process field (gaussian_process.py:127 divides the displacement by 10000 and the
+   derived quantities of GPVectorField.py inherit that scale); 1 for a plain RBF field v(x) = K(x, X_ctrl) C (the SparseVFC
+   field of sparsevfc.py:189-198, evaluated with nonrigid_only = 1, unit scales, zero means). */
 typedef struct spb_field_desc {
   int32_t D;
   int32_t K;
@@ -300,10 +303,11 @@ typedef struct spb_field_desc {
   double mean_fixed[3];
   double R[9];
   double t[3];
+  double velocity_divisor;
 } spb_field_desc;
 int spb_sizeof_field_desc(void);
 /* Differential geometry of the field at n raw query points X:[n][D] (device doubles), one pass, any output may be NULL:
-   V[n][D] velocity (x_new - x)/10000, J[n][D][D] analytical Jacobian, acc[n] / acc_mat[n][D] = J v, curvature
+   V[n][D] velocity (x_new - x)/velocity_divisor, J[n][D][D] analytical Jacobian, acc[n] / acc_mat[n][D] = J v, curvature
    (formula 1 or 2; curv_mat only for 2), curl ([n] in 2-D, [n][3] in 3-D), torsion[n][3] (3-D only), div[n], det[n].
    z, Coff: [K][D] device doubles; f is a HOST pointer. */
 int spb_field_geometry(const spb_field_desc* f, const double* X, int64_t n, const double* z, const double* Coff,

@@ -97,7 +97,7 @@ __global__ void field_geometry_kernel(spb_field_desc f, const double* __restrict
   for (int a = 0; a < D; ++a)
 #pragma unroll
     for (int b = 0; b < D; ++b) J[a][b] *= jscale;
-  // velocity in raw units / 10000
+  // velocity in raw units / velocity_divisor (10000 for the GP field, 1 for a plain RBF field)
   double v[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) {
@@ -109,7 +109,7 @@ __global__ void field_geometry_kernel(spb_field_desc f, const double* __restrict
       for (int e = 0; e < D; ++e) r += xn[e] * f.R[d * 3 + e];
       v[d] = (vel[d] + r) * f.scale_fixed + f.mean_fixed[d] - x[d];
     }
-    v[d] /= 10000.0;
+    v[d] /= f.velocity_divisor;
   }
   double a[D], vv = 0.0, va = 0.0, aa = 0.0;
 #pragma unroll

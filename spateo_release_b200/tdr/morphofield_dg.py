@@ -7,8 +7,11 @@ acceleration / curvature / curl / torsion / divergence in further per-cell loops
 registers; the Python layer only reproduces the reference's names, argument meaning, output shapes (including its
 broadcast quirks for the 3-D curl and the torsion) and where results are stored on the AnnData.
 
-Only the ``gaussian_process`` field is served here; ``method == "sparsevfc"`` goes to the third-party ``dynamo``
-``SvcVectorField`` in the reference (differential_geometry.py:25-29) and is out of scope.
+``method == "sparsevfc"`` goes to the third-party ``dynamo`` ``SvcVectorField`` in the reference
+(differential_geometry.py:24-28; dynamo-release>=1.4.1 is not vendored: **parity unpinned**). ``SvcVectorField`` below
+restates what that class evaluates for a SparseVFC field — v(x) = K(x, X_ctrl) C with the Gaussian kernel and its analytical
+Jacobian -2 beta sum_m K_m C_m (x - c_m)^T (dynamo's ``Jacobian_rkhs_gaussian``) — on the same kernel; the derived
+quantities are the formulas GPVectorField.py took over from dynamo.
 """
 
 from __future__ import annotations
@@ -38,6 +41,25 @@ def _desc(vf_dict: dict, D: int, nonrigid_only: bool, formula: int) -> "_capi.Sp
         f.mean_transformed[d], f.mean_fixed[d], f.t[d] = mt[d], mf[d], t[d]
         for e in range(D):
             f.R[d * 3 + e] = R[d, e]
+    f.velocity_divisor = 10000.0  # gaussian_process.py:127
+    return f
+
+
+def _is_svc(vf_dict: dict) -> bool:
+    return vf_dict.get("method") == "sparsevfc" or ("X_ctrl" in vf_dict and "inducing_variables" not in vf_dict)
+
+
+def _desc_svc(vf_dict: dict, D: int, formula: int) -> "_capi.SpbFieldDesc":
+    """A SparseVFC field v(x) = K(x, X_ctrl) C in raw coordinates: the plain RBF part of the kernel (nonrigid_only with unit
+    scales and zero means), velocity not divided."""
+    f = _capi.SpbFieldDesc()
+    f.D, f.K = D, int(np.asarray(vf_dict["X_ctrl"]).shape[0])
+    f.nonrigid_only, f.curvature_formula = 1, int(formula)
+    f.beta = float(vf_dict["beta"])
+    f.scale_transformed = f.scale_fixed = 1.0
+    for d in range(D):
+        f.R[d * 3 + d] = 1.0
+    f.velocity_divisor = 1.0
     return f
 
 
@@ -48,7 +70,10 @@ def field_geometry(X: np.ndarray, vf_dict: dict, want=("V", "J"), nonrigid_only:
 
     _capi.require_cuda()
     lib = _capi.load_library()
-    if vf_dict["kernel_type"] != "euc":
+    svc = _is_svc(vf_dict)
+    if svc and "div_cur_free_kernels" in vf_dict:
+        raise NotImplementedError("divergence/curl-free kernels are not implemented")
+    if not svc and vf_dict["kernel_type"] != "euc":
         if vf_dict["kernel_type"] == "geodist":
             raise NotImplementedError("geodist is not implemented yet")
         raise ValueError("current only support euc and geodist")
@@ -61,11 +86,14 @@ def field_geometry(X: np.ndarray, vf_dict: dict, want=("V", "J"), nonrigid_only:
     if "torsion" in want and D != 3:
         raise Exception("torsion is only defined in 3 dimension.")
     dev = torch.device("cuda" if device in (None, "cuda") else (f"cuda:{device}" if str(device).isdigit() else device))
-    f = _desc(vf_dict, D, nonrigid_only, formula)
+    f = _desc_svc(vf_dict, D, formula) if svc else _desc(vf_dict, D, nonrigid_only, formula)
+    zk, ck = ("X_ctrl", "C") if svc else ("inducing_variables", "Coff")
+    if np.asarray(vf_dict[zk]).shape[1] != D or np.asarray(vf_dict[ck]).shape[1] != D:
+        raise ValueError("X has incorrect dimensions.")
     with torch.cuda.device(dev):
         Xd = torch.from_numpy(X).to(dev)
-        z = torch.from_numpy(np.ascontiguousarray(vf_dict["inducing_variables"], dtype=np.float64)).to(dev)
-        C = torch.from_numpy(np.ascontiguousarray(vf_dict["Coff"], dtype=np.float64)).to(dev)
+        z = torch.from_numpy(np.ascontiguousarray(vf_dict[zk], dtype=np.float64)).to(dev)
+        C = torch.from_numpy(np.ascontiguousarray(vf_dict[ck], dtype=np.float64)).to(dev)
         shapes = {"V": (n, D), "J": (n, D, D), "acc": (n,), "acc_mat": (n, D), "curv": (n,), "curv_mat": (n, D),
                   "curl": (n,) if D == 2 else (n, 3), "torsion": (n, 3), "div": (n,), "det": (n,)}
         bufs = {k: (torch.empty(shapes[k], dtype=torch.float64, device=dev) if k in want else None) for k in _OUTPUTS}
@@ -169,6 +197,23 @@ class GPVectorField:
         return None  # the reference falls through for any other method
 
 
+class SvcVectorField(GPVectorField):
+    """What the reference takes from ``dynamo.vectorfield.scVectorField.SvcVectorField`` (differential_geometry.py:24-28)
+    for a field learned by ``morphofield_sparsevfc``: velocity K(x, X_ctrl) C, analytical Jacobian, and the same derived
+    quantities (acceleration J v, curvature, curl, torsion, divergence) — one kernel launch each. Parity unpinned (dynamo is
+    third-party and absent); checked against the float64 restatement in ``oracle/field_oracle.py``."""
+
+    def from_adata(self, adata, basis=None, vf_key: str = "VecFld", nonrigid_only: bool = False):
+        super().from_adata(adata, vf_key=vf_key, nonrigid_only=False)
+        if not _is_svc(self.vf_dict):
+            raise Exception(f"``anndata.uns[{vf_key}]`` does not hold a sparsevfc field (X_ctrl / C / beta).")
+
+    def get_Jacobian(self, method: str = "analytical", **kwargs) -> Callable:
+        if method == "analytical":
+            return lambda x: Jacobian_GP_gaussian_kernel(X=x, vf_dict=self.vf_dict)
+        raise NotImplementedError("only the analytical Jacobian is available (the numerical one needs numdifftools)")
+
+
 def _generate_vf_class(adata, vf_key: str, method: str = "gaussian_process", nonrigid_only: bool = False):
     """differential_geometry.py:12-39."""
     if vf_key in adata.uns.keys():
@@ -176,10 +221,8 @@ def _generate_vf_class(adata, vf_key: str, method: str = "gaussian_process", non
             vector_field_class = GPVectorField()
             vector_field_class.from_adata(adata, vf_key=vf_key, nonrigid_only=nonrigid_only)
         elif method == "sparsevfc":
-            raise NotImplementedError(
-                "differential geometry of a sparsevfc field is served by dynamo's SvcVectorField in the reference "
-                "(third-party, absent); only the gaussian_process field is supported here."
-            )
+            vector_field_class = SvcVectorField()
+            vector_field_class.from_adata(adata, basis=None, vf_key=vf_key)
         else:
             raise Exception(
                 f"The {method} is not in ``anndata.uns[{vf_key}]``."

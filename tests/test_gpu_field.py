@@ -90,3 +90,71 @@ def test_differential_geometry_wrappers_store_like_reference(golden):
     assert rel(a.obs["jacobian"].values, dets) < 1e-9
     b = dg.morphofield_divergence(a, key_added="div2", inplace=False)
     assert "div2" in b.obs and "div2" not in a.obs
+
+
+@pytest.mark.parametrize("D", [2, 3])
+def test_sparsevfc_field_geometry(D):
+    """differential_geometry.py:24-28 — a field learned by morphofield_sparsevfc (dynamo's SvcVectorField in the reference;
+    parity unpinned): velocity, Jacobian and every derived quantity against the float64 restatement, through the class and
+    through the st.tdr wrappers."""
+    from oracle import field_oracle as fo
+    from spateo_release_b200.tdr import morphofield_dg as dg
+
+    rng = np.random.default_rng(11 + D)
+    n, M = 300, 40
+    X = rng.uniform(0, 50, (n, D))
+    vf = {"X_ctrl": rng.uniform(0, 50, (M, D)), "C": rng.normal(size=(M, D)), "beta": 1.0 / 12.0**2, "method": "sparsevfc"}
+    want = fo.svc_geometry(X, vf)
+    vf["X"], vf["V"] = X, want["V"]
+    a = _Adata(n)
+    a.uns["VecFld_morpho"] = vf
+    c = dg._generate_vf_class(a, "VecFld_morpho", method="sparsevfc")
+    assert isinstance(c, dg.SvcVectorField)
+    assert rel(c.func(X), want["V"]) < 1e-12
+    assert rel(c.get_Jacobian()(X), want["J"]) < 1e-11
+    assert rel(c.get_Jacobian()(X[2]), want["J"][:, :, 2]) < 1e-11
+    acc, acc_mat = c.compute_acceleration()
+    assert rel(acc, want["acc"]) < 1e-10 and rel(acc_mat, want["acc_mat"]) < 1e-10
+    c2, c2m = c.compute_curvature(formula=2)
+    assert rel(c2, want["curv2"]) < 1e-9 and rel(c2m, want["curv2_mat"]) < 1e-9
+    assert rel(c.compute_curvature(formula=1)[0], want["curv1"]) < 1e-9
+    curl = c.compute_curl()
+    assert curl.shape == want["curl"].shape and rel(curl, want["curl"]) < 1e-11
+    assert rel(c.compute_divergence(), want["div"]) < 1e-11
+    if D == 3:
+        assert rel(c.compute_torsion(), want["torsion"]) < 1e-9
+    with pytest.raises(NotImplementedError):
+        c.compute_acceleration(method="numerical")
+    dg.morphofield_velocity(a)
+    dg.morphofield_acceleration(a)
+    dg.morphofield_divergence(a)
+    dg.morphofield_jacobian(a)
+    assert rel(a.obsm["velocity"], want["V"]) < 1e-12 and rel(a.obs["acceleration"].values, want["acc"]) < 1e-10
+    assert rel(a.obs["divergence"].values, want["div"]) < 1e-11
+    assert rel(a.uns["jacobian"], want["J"]) < 1e-11 and rel(a.obs["jacobian"].values, want["det"]) < 1e-9
+
+
+def test_sparsevfc_field_geometry_after_fit():
+    """End to end: st.tdr.morphofield_sparsevfc -> differential geometry of the stored field (keys X_ctrl / C / beta)."""
+    from oracle import field_oracle as fo
+    from spateo_release_b200 import tdr
+    from spateo_release_b200.tdr import morphofield_dg as dg
+
+    rng = np.random.default_rng(3)
+    n = 1500
+    X = rng.uniform(0, 60, (n, 3))
+    c = X - 30.0
+    V = np.stack([-0.05 * c[:, 1], 0.05 * c[:, 0], 0.02 * c[:, 2]], axis=1) + rng.normal(0, 0.05, (n, 3))
+    a = _Adata(n)
+    a.obsm["spatial"], a.obsm["V"] = X, V
+    vf = tdr.sparsevfc.SparseVFC(X, V, Grid=None, M=60, lambda_=0.02, MaxIter=30, device="0")
+    vf["method"] = "sparsevfc"
+    a.uns["VecFld_morpho"] = vf
+    want = fo.svc_geometry(vf["X"], {k: np.asarray(vf[k]) for k in ("X_ctrl", "C")} | {"beta": vf["beta"]})
+    dg.morphofield_curl(a)
+    dg.morphofield_divergence(a)
+    assert rel(a.obsm["curl"], want["curl"]) < 1e-9 and rel(a.obs["divergence"].values, want["div"]) < 1e-9
+    # the fitted field is a rotation about z (+ stretch along z): curl_z ~ 0.1, divergence ~ 0.02 in the interior
+    inner = (np.abs(c) < 15).all(1)
+    assert abs(np.median(a.obsm["curl"][inner, 0, 2]) - 0.1) < 0.03
+    assert abs(np.median(a.obs["divergence"].values[inner]) - 0.02) < 0.02

@@ -168,3 +168,32 @@ def test_segment_choice_respects_the_column_cap(monkeypatch):
     seg2 = Morpho_pairwise._choose_segments(98, 100000)
     assert seg2 > seg and (100000 + seg2 - 1) // seg2 <= 1024
     assert Morpho_pairwise._choose_segments(1, 240) >= 1
+
+
+def test_svc_field_descriptor_and_oracle_jacobian():
+    """The SparseVFC field rides on the GP kernel as its plain RBF part (unit scales, zero means, velocity not divided);
+    the float64 restatement of its Jacobian is the derivative of its velocity (central differences)."""
+    from oracle import field_oracle as fo
+    from spateo_release_b200.tdr import morphofield_dg as dg
+
+    rng = np.random.default_rng(5)
+    vf = {"X_ctrl": rng.uniform(0, 10, (7, 3)), "C": rng.normal(size=(7, 3)), "beta": 0.08, "method": "sparsevfc"}
+    f = dg._desc_svc(vf, 3, 2)
+    assert (f.D, f.K, f.nonrigid_only, f.velocity_divisor) == (3, 7, 1, 1.0)
+    assert f.scale_fixed == f.scale_transformed == 1.0 and list(f.mean_transformed) == [0.0] * 3 and f.beta == 0.08
+    assert dg._is_svc(vf) and not dg._is_svc({"inducing_variables": 1, "Coff": 2, "method": "gaussian_process"})
+    gp = {"inducing_variables": vf["X_ctrl"], "Coff": vf["C"], "beta": 0.08, "kernel_type": "euc", "R": np.eye(3),
+          "t": np.zeros(3), "norm_dict": {"mean_transformed": np.zeros(3), "mean_fixed": np.zeros(3),
+                                          "scale_transformed": 1.0, "scale_fixed": 1.0}}
+    assert dg._desc(gp, 3, False, 2).velocity_divisor == 10000.0
+    X = rng.uniform(0, 10, (6, 3))
+    g = fo.svc_geometry(X, vf)
+    # with unit scales the GP restatement's non-rigid part is the same field / 10000 and the same Jacobian
+    assert np.allclose(fo.gp_velocity(X, gp, nonrigid_only=True) * 10000, g["V"], rtol=1e-12, atol=0)
+    assert np.allclose(fo.jacobian(X, gp), g["J"], rtol=1e-12, atol=1e-15)
+    h = 1e-5
+    for j in range(3):
+        e = np.zeros(3); e[j] = h
+        fd = (fo.svc_velocity(X + e, vf) - fo.svc_velocity(X - e, vf)) / (2 * h)   # d v_i / d x_j for every point
+        assert np.allclose(g["J"][:, j, :].T, fd, rtol=1e-6, atol=1e-9)
+    assert np.allclose(g["div"], np.einsum("iin->n", g["J"]))
