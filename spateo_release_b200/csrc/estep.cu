@@ -11,8 +11,10 @@
 //   row_finalize   reduces the per-segment partials in fp64 and forms the global sums.
 //
 // Algorithmic HBM traffic: 4 bytes per cell pair per sweep (the fp32 g_ij), 8 B/pair/iteration in total.
-// Thread mapping: 256 consumer threads own 4 consecutive rows each (one float4 of a GT row), one extra warp is the
-// bulk-copy producer. Column constants are broadcast from shared memory.
+// Thread mapping: a CTA covers SPB_ROW_TILE = 512 moving cells: 128 consumer threads own 4 consecutive rows each (one
+// float4 of a GT row), one extra warp is the bulk-copy producer (160 threads, 96 registers, ~50 KB of shared memory:
+// 4 CTAs per SM). Column constants are broadcast from shared memory. 512-row tiles replaced the 1024-row tiles of
+// round 1: same dense speed, finer exact culling and shorter tails (profiles/launches_r02_full_summary.md).
 #include "common.cuh"
 
 namespace {
