@@ -600,13 +600,16 @@ class Morpho_pairwise:
         ib = np.random.choice(self.NB, n_sampling, replace=False) if self.NB > n_sampling else np.arange(self.NB)
         cA, cB = self.coordsA[ia, :], self.coordsB[ib, :]
         N, M, D = cA.shape[0], cB.shape[0], cA.shape[1]
+        import time as _time
+
+        _t = _time.perf_counter()
         XA = self._device_rows(self.init_layer, self.init_field, "A", ia)
         XB = self._device_rows(self.init_layer, self.init_field, "B", ib)
         if XA is None or XB is None:  # an initialisation layer that is not part of the alignment: host extraction
             XA = U.get_rep(self.sampleA[ia], self.init_layer, self.init_field, self.genes, self._np_dtype)
             XB = U.get_rep(self.sampleB[ib], self.init_layer, self.init_field, self.genes, self._np_dtype)
-        import time as _time
-
+        # the first use of the representations uploads them (staged H2D of both expression matrices) — the one upload of a run
+        self._timing["coarse.upload_and_gather_s"] = _time.perf_counter() - _t
         _t = _time.perf_counter()
         cA, XA = self._voxel_data_device(cA, XA, voxel_num=max(min(int(N / 20), 1000), 100))
         cB, XB = self._voxel_data_device(cB, XB, voxel_num=max(min(int(M / 20), 1000), 100))
