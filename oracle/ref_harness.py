@@ -120,3 +120,18 @@ def load_reference_transform():
             setattr(pkg, name, getattr(utils, name, None))
     _loaded["tr"] = importlib.import_module("spateo.alignment.transform")
     return _loaded["tr"]
+
+
+def load_reference_drivers():
+    """The unmodified ``spateo/alignment/morpho_alignment.py`` (morpho_align, morpho_align_transformation,
+    morpho_align_apply_transformation). Its ``from spateo.alignment.methods import Morpho_pairwise, empty_cache`` is served
+    from the already-imported leaf modules; ``spateo.alignment.transform`` / ``utils`` are imported unmodified."""
+    if "drv" in _loaded:
+        return _loaded["drv"]
+    mc, utils = load_reference()
+    load_reference_transform()
+    pkg = sys.modules["spateo.alignment.methods"]
+    pkg.Morpho_pairwise = mc.Morpho_pairwise
+    pkg.empty_cache = utils.empty_cache
+    _loaded["drv"] = importlib.import_module("spateo.alignment.morpho_alignment")
+    return _loaded["drv"]

@@ -145,3 +145,48 @@ def test_gather_transformations_under_nccl_resolves_index_strings():
             assert np.allclose(out[2]["Translation"], [2.0, -2.0])
     finally:
         dist.destroy_process_group()
+
+
+def _rel_coords(a, b):
+    return float(np.abs(np.asarray(a, dtype=np.float64) - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("mode", ["SN-S", "SN-N"])
+def test_morpho_align_driver_matches_reference_driver(golden, mode):
+    """``st.align.morpho_align`` (serial chain: pair i+1 starts from pair i's aligned coordinates, morpho_alignment.py:66-111)
+    against the UNMODIFIED reference driver on the same four slices (tests/golden/make_golden_drivers.py): every slice's
+    rigid / non-rigid / final placement within 1e-3 of the coordinate range, same uns keys, same pi shapes."""
+    import spateo_release_b200 as st
+    from driver_helpers import KW, models_from_golden
+
+    g = golden("drivers")
+    tag = mode.replace("-", "")
+    np.random.seed(0)
+    aligned, pis = st.align.morpho_align(models_from_golden(g), mode=mode, device="0", verbose=False, **KW)
+    assert [tuple(p.shape) for p in pis] == [tuple(s) for s in g[f"{tag}_pi_shapes"]]
+    assert sorted(aligned[1].uns.keys()) == list(g[f"{tag}_uns_keys_1"])
+    for k in range(4):
+        for key in ("align_spatial", "align_spatial_rigid", "align_spatial_nonrigid"):
+            err = _rel_coords(aligned[k].obsm[key], g[f"{tag}_{k}_{key}"])
+            assert err < 1e-3, (k, key, err)
+    sums = np.array([float(np.asarray(p, dtype=np.float64).sum()) for p in pis])
+    assert np.allclose(sums, g[f"{tag}_pi_sums"], rtol=2e-2)
+
+
+def test_transformation_chain_matches_reference_driver(golden):
+    """``morpho_align_transformation`` + ``morpho_align_apply_transformation`` (independent pairs on raw coordinates, composed;
+    morpho_alignment.py:181-217, 284-303) against the reference driver's links and placements."""
+    import spateo_release_b200 as st
+    from driver_helpers import KW, models_from_golden
+
+    g = golden("drivers")
+    ms = models_from_golden(g)
+    np.random.seed(0)
+    tr = st.align.morpho_align_transformation(ms, device="0", verbose=False, **KW)
+    assert len(tr) == 3
+    for i, t in enumerate(tr):
+        assert np.abs(np.asarray(t["Rotation"]) - g[f"tr{i}_Rotation"]).max() < 1e-4, i
+        assert np.abs(np.asarray(t["Translation"]) - g[f"tr{i}_Translation"]).max() < 1e-3 * np.abs(g["in0_spatial"]).max(), i
+    placed = st.align.morpho_align_apply_transformation(ms, transformation=tr, verbose=False)
+    for k in range(4):
+        assert _rel_coords(placed[k].obsm["align_spatial"], g[f"placed{k}"]) < 1e-3, k

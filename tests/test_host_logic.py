@@ -197,3 +197,33 @@ def test_svc_field_descriptor_and_oracle_jacobian():
         fd = (fo.svc_velocity(X + e, vf) - fo.svc_velocity(X - e, vf)) / (2 * h)   # d v_i / d x_j for every point
         assert np.allclose(g["J"][:, j, :].T, fd, rtol=1e-6, atol=1e-9)
     assert np.allclose(g["div"], np.einsum("iin->n", g["J"]))
+
+
+def test_apply_transformation_matches_reference_driver(golden):
+    """morpho_align_apply_transformation / compose_transformations against the UNMODIFIED reference driver's output
+    (tests/golden/make_golden_drivers.py; morpho_alignment.py:284-303): host-only code, identical arithmetic order."""
+    from driver_helpers import models_from_golden
+    from spateo_release_b200.alignment import morpho_alignment as ma
+
+    g = golden("drivers")
+    tr = [{"Rotation": g[f"tr{i}_Rotation"], "Translation": g[f"tr{i}_Translation"]} for i in range(3)]
+    placed = ma.morpho_align_apply_transformation(models_from_golden(g), transformation=tr, verbose=False)
+    for k in range(4):
+        assert np.array_equal(np.asarray(placed[k].obsm["align_spatial"]), g[f"placed{k}"]), k
+    # every link of the golden is a proper 2-D rotation, and slice 0 is left where it was
+    for t in tr:
+        assert np.allclose(t["Rotation"] @ t["Rotation"].T, np.eye(2), atol=1e-6) and np.linalg.det(t["Rotation"]) > 0
+    assert np.array_equal(g["placed0"], g["in0_spatial"])
+
+
+def test_solve_RT_by_correspondence_reproduces_reference_links(golden):
+    """The link of pair i is solve_RT_by_correspondence(optimal_RnA[:, :2], raw[:, :2]) (morpho_alignment.py:205-207). The
+    serial driver's rigid output of slice 1 is the same pair solved on the same coordinates, so the golden's own arrays pin
+    our solver: rotating/translating the raw slice with the stored link must land on the stored rigid placement."""
+    from spateo_release_b200.alignment import utils as AU
+
+    g = golden("drivers")
+    raw1, rigid1 = g["in1_spatial"], g["SNS_1_align_spatial_rigid"]
+    R, t = AU.solve_RT_by_correspondence(rigid1, raw1)
+    assert np.allclose(R, g["tr0_Rotation"], atol=1e-6) and np.allclose(t, g["tr0_Translation"], atol=1e-4)
+    assert np.abs(raw1 @ R.T + t - rigid1).max() < 1e-3
