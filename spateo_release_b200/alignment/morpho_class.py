@@ -350,6 +350,9 @@ class Morpho_pairwise:
         self.compute_mapping = compute_mapping
         self.spatial_sort, self.cull_zero_tiles = spatial_sort, cull_zero_tiles
         self.use_cuda_graph = os.environ.get("SPB_CUDA_GRAPH", "1") != "0"
+        # iterations per captured graph: light iterations (SVI batches, small pairs) are bound by the host's graph launches
+        # on a slow host, so several identical iterations ride in one graph; 0 = choose from the pairs per iteration
+        self.graph_unroll = int(os.environ.get("SPB_GRAPH_UNROLL", "0"))
         # column-sharded pair: (rank, world, mode) — this process holds the fixed cells [NB * rank / world, NB * (rank + 1) /
         # world) of ONE pair; see alignment/distributed.py:morpho_align_pair_sharded
         self.column_shard = column_shard
@@ -1352,11 +1355,22 @@ class Morpho_pairwise:
                             # device, and doing it here keeps the host free to enqueue the whole run without stopping
                             check(self._lib.spb_nonrigid_warm(), "spb_nonrigid_warm")
                             self._iteration_graph(True)
+                            if self._graph_unroll() > 1 and end - self.nonrigid_start_iter - 2 >= 2 * self._graph_unroll():
+                                self._iteration_graph(True, self._graph_unroll())
+                        n_rep = stop - it - 1
+                        unroll = self._graph_unroll()
+                        replayed = 0
+                        if unroll > 1 and n_rep >= 2 * unroll:
+                            graph_u, n_kernels_u = self._iteration_graph(nonrigid, unroll)
+                            for _ in range(n_rep // unroll):
+                                graph_u.replay()
+                            replayed += n_kernels_u * (n_rep // unroll)
+                            n_rep -= (n_rep // unroll) * unroll
                         graph, n_kernels = self._iteration_graph(nonrigid)
-                        for _ in range(it + 1, stop):
+                        for _ in range(n_rep):
                             graph.replay()
                         # kernels launched through graph replays are not seen by the library's launch counter
-                        self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + n_kernels * (stop - it - 1)
+                        self.graph_replayed_launches = getattr(self, "graph_replayed_launches", 0) + replayed + n_kernels * n_rep
                         it = stop
                         continue
                 if hist is not None:
@@ -1369,17 +1383,30 @@ class Morpho_pairwise:
                     torch.cuda.nvtx.range_pop()
                 it += 1
 
-    def _iteration_graph(self, nonrigid: bool):
-        """CUDA graph of one EM iteration of the given phase (captured once per device state)."""
+    def _graph_unroll(self) -> int:
+        """Iterations per captured graph: 8 when an iteration touches fewer than 2e9 cell pairs (about 2 ms of device time:
+        the default SVI batch of the 100k pair, or any small pair), where one graph launch per iteration can make a slow
+        host the bottleneck; 1 for the heavy full-EM iterations."""
+        u = getattr(self, "graph_unroll", 0)
+        if u > 0:
+            return u
+        cols = self.batch_size if self.SVI_mode else self.NB
+        return 8 if float(self.NA) * float(cols) < 2e9 else 1
+
+    def _iteration_graph(self, nonrigid: bool, unroll: int = 1):
+        """CUDA graph of ``unroll`` consecutive EM iterations of the given phase (captured once per device state; the
+        iteration index is a device counter, so the copies are identical launch sequences)."""
         graphs = self.__dict__.setdefault("_graphs", {})
-        if nonrigid not in graphs:
+        key = (bool(nonrigid), int(unroll))
+        if key not in graphs:
             g = torch.cuda.CUDAGraph()
             n0 = self._lib.spb_launch_count()
             with torch.cuda.graph(g):
-                check(self._lib.spb_em_iteration_ex(C.byref(self._params), -1, 1 if nonrigid else 0, _capi.current_stream_ptr()),
-                      "spb_em_iteration_ex(capture)")
-            graphs[nonrigid] = (g, int(self._lib.spb_launch_count() - n0))
-        return graphs[nonrigid]
+                for _ in range(unroll):
+                    check(self._lib.spb_em_iteration_ex(C.byref(self._params), -1, 1 if nonrigid else 0,
+                                                        _capi.current_stream_ptr()), "spb_em_iteration_ex(capture)")
+            graphs[key] = (g, int(self._lib.spb_launch_count() - n0))
+        return graphs[key]
 
     @torch.no_grad()
     def run(self):
