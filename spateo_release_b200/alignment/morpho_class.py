@@ -245,7 +245,7 @@ class Morpho_pairwise:
     N_A x N_B posterior (40 GB at 100k x 100k) and returns None; every other output is unaffected.
     ``compute_mapping`` — ``self.mapping`` (an ``ArgmaxPi``) receives the row / column maxima of the final posterior from a
     fused kernel, for ``get_optimal_mapping_relationship`` / ``mapping_aligned_coords`` without a dense P.
-    ``spatial_sort`` / ``cull_zero_tiles`` — the moving cells are processed in Morton order so that each 1024-row block is
+    ``spatial_sort`` / ``cull_zero_tiles`` — the moving cells are processed in Morton order so that each row block (SPB_ROW_TILE = 512 cells) is
     spatially compact, and (row block, fixed cell) tiles whose every pair underflows to exactly 0 in fp32 are skipped;
     results are bit-identical to the dense sweep (all outputs are returned in the caller's row order).
     ``column_shard`` — set by ``morpho_align_pair_sharded``: one pair's fixed cells split over several GPUs.

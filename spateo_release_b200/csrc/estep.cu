@@ -857,7 +857,7 @@ struct SelShared {
 };
 
 // histogram of (key >> shift) & (nb - 1) over the values whose key matches (prefix, pmask); zero weights are skipped
-// mask (optional): bit rb set <=> row block rb (1024 rows) can hold a non-zero weight for this column; the other blocks
+// mask (optional): bit rb set <=> row block rb (SPB_ROW_TILE rows) can hold a non-zero weight for this column; the other blocks
 // are provably all-zero (build_col_lists_kernel) and are skipped — a warp never straddles two row blocks
 template <typename F>
 __device__ __forceinline__ void sel_for_each(const float* __restrict__ g, const float* __restrict__ XA, int64_t ldx,

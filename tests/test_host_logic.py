@@ -227,3 +227,17 @@ def test_solve_RT_by_correspondence_reproduces_reference_links(golden):
     R, t = AU.solve_RT_by_correspondence(rigid1, raw1)
     assert np.allclose(R, g["tr0_Rotation"], atol=1e-6) and np.allclose(t, g["tr0_Translation"], atol=1e-4)
     assert np.abs(raw1 @ R.T + t - rigid1).max() < 1e-3
+
+
+def test_graph_unroll_choice():
+    """Iterations per captured CUDA graph: 8 for light iterations (default SVI batch of the 100k pair, small pairs), 1 for
+    the heavy full-EM iterations; an explicit value (SPB_GRAPH_UNROLL / attribute) wins."""
+    from types import SimpleNamespace
+
+    from spateo_release_b200.alignment.morpho_class import Morpho_pairwise
+
+    f = Morpho_pairwise._graph_unroll
+    assert f(SimpleNamespace(graph_unroll=0, SVI_mode=False, NA=100000, NB=100000, batch_size=None)) == 1
+    assert f(SimpleNamespace(graph_unroll=0, SVI_mode=True, NA=100000, NB=100000, batch_size=10000)) == 8
+    assert f(SimpleNamespace(graph_unroll=0, SVI_mode=False, NA=5000, NB=5000, batch_size=None)) == 8
+    assert f(SimpleNamespace(graph_unroll=3, SVI_mode=False, NA=100000, NB=100000, batch_size=None)) == 3
